@@ -1,0 +1,110 @@
+"""ctypes loader for the CPU oracle (oracle/field_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: importable from tests/, __graft_entry__.smoke() and bench.py's CPU
+baseline legs.  The product package (gstools-core_b200/) never imports this.
+
+Functions mirror the reference's Python names (src/lib.rs:34,51,68) so parity tests read like the
+reference's own: summate / summate_incompr / summate_fourier, numpy in, numpy out.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libgsf_oracle.so")
+_lib = None
+
+_i64 = ctypes.c_int64
+_dp = ctypes.c_void_p
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle with the committed recipe (oracle/Makefile)."""
+    src = os.path.join(_HERE, "field_oracle.c")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", _HERE, "-B" if force else "-s"], check=True,
+                       stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = ctypes.CDLL(_LIB_PATH)
+        common = [ctypes.c_int, _i64, _i64]
+        arr2 = [_dp, _i64, _i64]
+        arr1 = [_dp, _i64]
+        L.gso_summator.argtypes = common + arr2 + arr1 + arr1 + arr2 + [_dp, ctypes.c_int]
+        L.gso_summator_incompr.argtypes = common + arr2 + arr1 + arr1 + arr2 + [_dp, ctypes.c_int]
+        L.gso_summator_fourier.argtypes = common + arr1 + arr2 + arr1 + arr1 + arr2 + [_dp, ctypes.c_int]
+        for f in (L.gso_summator, L.gso_summator_incompr, L.gso_summator_fourier, L.gso_max_threads):
+            f.restype = ctypes.c_int
+        _lib = L
+    return _lib
+
+
+def _a(x, ndim):
+    x = np.asarray(x)
+    if x.dtype != np.float64 or x.ndim != ndim:
+        raise TypeError("oracle expects float64 arrays of rank %d" % ndim)
+    return x
+
+
+def _s(x):
+    return [x.ctypes.data] + [s // 8 for s in x.strides]
+
+
+def _check(cov, z1, z2, pos):
+    if cov.shape[0] != pos.shape[0] or cov.shape[1] != z1.shape[0] or cov.shape[1] != z2.shape[0]:
+        raise ValueError("shape mismatch (reference: assert_eq!, src/field.rs:44-46)")
+
+
+def max_threads() -> int:
+    return lib().gso_max_threads()
+
+
+def summate(cov_samples, z1, z2, pos, num_threads=None):
+    cov, z1, z2, pos = _a(cov_samples, 2), _a(z1, 1), _a(z2, 1), _a(pos, 2)
+    _check(cov, z1, z2, pos)
+    d, n = cov.shape
+    m = pos.shape[1]
+    out = np.empty(m, dtype=np.float64)
+    rc = lib().gso_summator(d, n, m, *_s(cov), *_s(z1), *_s(z2), *_s(pos), out.ctypes.data,
+                            int(num_threads or 1))
+    if rc:
+        raise ValueError("oracle summator failed rc=%d" % rc)
+    return out
+
+
+def summate_incompr(cov_samples, z1, z2, pos, num_threads=None):
+    cov, z1, z2, pos = _a(cov_samples, 2), _a(z1, 1), _a(z2, 1), _a(pos, 2)
+    _check(cov, z1, z2, pos)
+    d, n = cov.shape
+    m = pos.shape[1]
+    out = np.empty((d, m), dtype=np.float64, order="F")  # src/field.rs:166-174
+    rc = lib().gso_summator_incompr(d, n, m, *_s(cov), *_s(z1), *_s(z2), *_s(pos),
+                                    out.ctypes.data, int(num_threads or 1))
+    if rc:
+        raise ValueError("oracle summator_incompr failed rc=%d" % rc)
+    return out
+
+
+def summate_fourier(spectrum_factor, modes, z1, z2, pos, num_threads=None):
+    sf = _a(spectrum_factor, 1)
+    cov, z1, z2, pos = _a(modes, 2), _a(z1, 1), _a(z2, 1), _a(pos, 2)
+    _check(cov, z1, z2, pos)
+    if sf.shape[0] != cov.shape[1]:
+        raise ValueError("spectrum_factor length mismatch")
+    d, n = cov.shape
+    m = pos.shape[1]
+    out = np.empty(m, dtype=np.float64)
+    rc = lib().gso_summator_fourier(d, n, m, *_s(sf), *_s(cov), *_s(z1), *_s(z2), *_s(pos),
+                                    out.ctypes.data, int(num_threads or 1))
+    if rc:
+        raise ValueError("oracle summator_fourier failed rc=%d" % rc)
+    return out
