@@ -1,0 +1,311 @@
+// gsf_kernels.cuh -- sm_100a kernels of the randomization-method field summation.
+//
+// Math.  The reference evaluates, per point x_j and mode k_i (src/field.rs:57-60,145-152,242-245)
+//     z1_i*cos(phi) + z2_i*sin(phi),   phi = <k_i, x_j>
+// which is  A_i * cos(phi - theta_i)  with  A_i = hypot(z1_i, z2_i), theta_i = atan2(z2_i, z1_i).
+// A pre-pass (gsf_prep_modes) converts every mode ONCE into half-turn units
+//     kh = k/pi,  th = theta/pi,  amplitude(s) A (times spectrum_factor / projector p_a(k)),
+// so the hot loop needs a single cos(pi*t), t = <kh, x> - th, per point*mode:
+//     t   : D DFMA                      (init with -th)
+//     r   : 3 DADD   n = rint(t) by the 1.5*2^52 trick, r = t - n exact, |r| <= 1/2
+//     s   : 1 DMUL   s = r*r
+//     u   : 6 DFMA   u = sqrt2*cos(pi/2 r), minimax deg-6 in s      (cospi_poly.cuh)
+//     y   : 1 DFMA   cos(pi r) = u*u - 1
+//     acc : NC DFMA  acc_a += (+-A_a) * y, sign = parity of n (integer XOR, not on the FP64 pipe)
+// = D + 11 + NC FP64-pipe instructions per point*mode (15 for the 3-D scalar field).
+//
+// Mapping.  One CTA = kThreads threads = a tile of P*kThreads/L points.  A group of L lanes shares
+// one point set and splits the modes (lane sub handles modes sub, sub+L, ...); partial sums are
+// combined with a fixed-order xor-shuffle tree.  L = 1 for large M (pure per-thread sums); L > 1
+// only widens small problems so all 148 SMs have work.  Mode records stream through a two-stage
+// shared-memory ring filled by 1-D TMA bulk copies (cp.async.bulk + mbarrier); with L = 1 every
+// LDS is a warp-wide broadcast.  Positions are read once per thread (coalesced, SoA rows).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "cospi_poly.cuh"
+
+namespace gsf {
+
+constexpr int kThreads = 128;     // threads per CTA
+constexpr int kModeBlock = 256;   // mode records per shared-memory stage
+constexpr int kStages = 2;
+constexpr double kMagic = 6755399441055744.0;  // 1.5 * 2^52
+
+enum Kind : int { kScalar = 0, kIncompr = 1, kFourier = 2 };
+
+// doubles per pre-processed mode record: kh[D], th, A[NC], padded to an even count so every
+// record (and every block of records) is a multiple of 16 bytes (TMA bulk-copy granularity).
+__host__ __device__ constexpr int rec_doubles(int D, int NC) { return (D + 1 + NC + 1) & ~1; }
+
+// ------------------------------------------------------------------------------------------
+// Mode pre-processing: one thread per mode.  Inputs are the caller's (possibly strided) arrays.
+struct PrepArgs {
+    const double *k;  int64_t ks0, ks1;     // (D, N)
+    const double *z1; int64_t z1s;
+    const double *z2; int64_t z2s;
+    const double *sf; int64_t sfs;          // nullptr unless fourier
+    double *rec;                            // N * rec_doubles
+    int64_t n_modes;
+    int dim;
+    int incompr;                            // NC = dim if set, else 1
+};
+
+// x * (1/pi) with 1/pi carried as a double-double: the result is the correctly rounded quotient
+// in all but ~1e-16 of cases, so kh adds no error beyond one rounding of k/pi.
+__device__ __forceinline__ double div_pi(double x)
+{
+    const double inv_pi_hi = 0x1.45f306dc9c883p-2;   // 0.31830988618379069
+    const double inv_pi_lo = -0x1.6b01ec5417056p-56; // 1/pi - inv_pi_hi
+    return fma(x, inv_pi_hi, __dmul_rn(x, inv_pi_lo));
+}
+
+__global__ void gsf_prep_modes(PrepArgs a)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n_modes) return;
+    const int D = a.dim;
+    const int NC = a.incompr ? D : 1;
+    const int R = rec_doubles(D, NC);
+    double *rec = a.rec + i * R;
+
+    const double z1 = a.z1[i * a.z1s];
+    const double z2 = a.z2[i * a.z2s];
+    double amp = hypot(z1, z2);
+    const double th = div_pi(atan2(z2, z1));
+    if (a.sf) amp = __dmul_rn(a.sf[i * a.sfs], amp);   // src/field.rs:243
+
+    double kk = 0.0;
+    for (int d = 0; d < D; ++d) {
+        const double kd = a.k[d * a.ks0 + i * a.ks1];
+        rec[d] = div_pi(kd);
+        kk = __dadd_rn(kk, __dmul_rn(kd, kd));          // ShortVec::dot, src/short_vec.rs:31-33
+    }
+    rec[D] = -th;                                       // the dot-product chain starts from -theta
+    if (!a.incompr) {
+        rec[D + 1] = amp;
+    } else {
+        // projector, src/field.rs:138,148,151:  k_2 = k0/|k|^2 ; p0 = 1 - k0*k_2 ; pa = -(ka*k_2)
+        const double k0 = a.k[i * a.ks1];
+        const double k_2 = __ddiv_rn(k0, kk);           // NaN for k = 0, as in the reference
+        rec[D + 1] = __dmul_rn(__dadd_rn(1.0, -__dmul_rn(k0, k_2)), amp);
+        for (int d = 1; d < D; ++d) {
+            const double kd = a.k[d * a.ks0 + i * a.ks1];
+            rec[D + 1 + d] = __dmul_rn(-__dmul_rn(kd, k_2), amp);
+        }
+    }
+    for (int d = D + 1 + NC; d < R; ++d) rec[d] = 0.0;
+}
+
+// ------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + 1-D bulk async copy (TMA engine; SASS: UBLKCP / SYNCS).
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// cos(pi*t) for the reduced argument, plus the sign bit (parity of rint(t)) as a word to XOR
+// into the high half of a double.  9 FP64-pipe instructions + 1 shift.
+__device__ __forceinline__ double cospi_core(double t, uint32_t &flip)
+{
+    const double tn = __dadd_rn(t, kMagic);     // low mantissa bits = rint(t)
+    const double nf = __dadd_rn(tn, -kMagic);   // rint(t) as a double
+    const double r = __dadd_rn(t, -nf);         // exact, |r| <= 1/2
+    const double s = __dmul_rn(r, r);
+    double u = GSF_U6;
+    u = fma(u, s, GSF_U5);
+    u = fma(u, s, GSF_U4);
+    u = fma(u, s, GSF_U3);
+    u = fma(u, s, GSF_U2);
+    u = fma(u, s, GSF_U1);
+    u = fma(u, s, GSF_U0);
+    flip = static_cast<uint32_t>(__double2loint(tn)) << 31;
+    return fma(u, u, -1.0);
+}
+
+__device__ __forceinline__ double xor_sign(double v, uint32_t flip)
+{
+    return __hiloint2double(__double2hiint(v) ^ static_cast<int>(flip), __double2loint(v));
+}
+
+struct SumArgs {
+    const double *rec;            // pre-processed mode records
+    int64_t n_modes;
+    const double *pos;            // element strides: pos[a*ps0 + j*ps1]
+    int64_t ps0, ps1;
+    int64_t n_points;
+    double *out;                  // out[a*os0 + j*os1]
+    int64_t os0, os1;
+};
+
+// D: spatial dimension; NC: accumulators per point (1 scalar/fourier, D incompr);
+// P: points per thread; L: lanes sharing one point (modes split over them).
+template <int D, int NC, int P, int L>
+__global__ void __launch_bounds__(kThreads) gsf_sum_kernel(SumArgs a)
+{
+    constexpr int R = rec_doubles(D, NC);
+    constexpr int kGroups = kThreads / L;            // point slots per CTA pass
+    constexpr int kTile = kGroups * P;               // points per CTA
+    __shared__ __align__(128) double s_rec[kStages][kModeBlock * R];
+    __shared__ __align__(8) uint64_t s_bar[kStages];
+
+    const int tid = threadIdx.x;
+    const int sub = tid % L;                         // which slice of the modes
+    const int grp = tid / L;                         // which point slot
+    const int64_t tile0 = (int64_t)blockIdx.x * kTile;
+
+    // ---- positions -> registers (coalesced: consecutive groups read consecutive points)
+    double x[P][D];
+    int64_t jpt[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        const int64_t j = tile0 + (int64_t)p * kGroups + grp;
+        jpt[p] = j;
+        const int64_t jc = j < a.n_points ? j : a.n_points - 1;   // clamp: tail lanes recompute
+#pragma unroll
+        for (int d = 0; d < D; ++d) x[p][d] = __ldg(a.pos + d * a.ps0 + jc * a.ps1);
+    }
+
+    double acc[P][NC];
+#pragma unroll
+    for (int p = 0; p < P; ++p)
+#pragma unroll
+        for (int c = 0; c < NC; ++c) acc[p][c] = 0.0;
+
+    // ---- mode ring: thread 0 is the producer
+    const int64_t n_blocks = (a.n_modes + kModeBlock - 1) / kModeBlock;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) mbar_init(&s_bar[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    auto issue = [&](int64_t b) {
+        const int st = (int)(b % kStages);
+        const int64_t m0 = b * kModeBlock;
+        const int64_t cnt = (a.n_modes - m0) < kModeBlock ? (a.n_modes - m0) : kModeBlock;
+        const uint32_t bytes = (uint32_t)(cnt * R * sizeof(double));
+        mbar_expect_tx(&s_bar[st], bytes);
+        bulk_g2s(&s_rec[st][0], a.rec + m0 * R, bytes, &s_bar[st]);
+    };
+    if (tid == 0) {
+        for (int64_t b = 0; b < kStages && b < n_blocks; ++b) issue(b);
+    }
+
+    for (int64_t b = 0; b < n_blocks; ++b) {
+        const int st = (int)(b % kStages);
+        const uint32_t parity = (uint32_t)((b / kStages) & 1);
+        mbar_wait(&s_bar[st], parity);
+        const int64_t m0 = b * kModeBlock;
+        const int cnt = (int)((a.n_modes - m0) < kModeBlock ? (a.n_modes - m0) : kModeBlock);
+        const double *blk = &s_rec[st][0];
+
+#pragma unroll 2
+        for (int i = sub; i < cnt; i += L) {
+            const double *m = blk + i * R;
+            double kh[D], nth, amp[NC];
+#pragma unroll
+            for (int d = 0; d < D; ++d) kh[d] = m[d];
+            nth = m[D];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) amp[c] = m[D + 1 + c];
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                double t = nth;
+#pragma unroll
+                for (int d = 0; d < D; ++d) t = fma(kh[d], x[p][d], t);
+                uint32_t flip;
+                const double y = cospi_core(t, flip);
+                if (NC == 1) {
+                    acc[p][0] = fma(xor_sign(amp[0], flip), y, acc[p][0]);
+                } else {
+                    const double ys = xor_sign(y, flip);
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) acc[p][c] = fma(amp[c], ys, acc[p][c]);
+                }
+            }
+        }
+        __syncthreads();                              // everyone is done with stage st
+        if (tid == 0 && b + kStages < n_blocks) issue(b + kStages);
+    }
+
+    // ---- combine the L mode slices (fixed-order butterfly), then one store per point
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            double v = acc[p][c];
+#pragma unroll
+            for (int o = L / 2; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            acc[p][c] = v;
+        }
+        if (sub == 0 && jpt[p] < a.n_points) {
+#pragma unroll
+            for (int c = 0; c < NC; ++c) a.out[c * a.os0 + jpt[p] * a.os1] = acc[p][c];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// DFMA peak micro-benchmark: kChains independent dependent-FMA chains per thread, all SMs at
+// full occupancy.  Each loop iteration issues kChains*kUnroll DFMAs and nothing else of note.
+constexpr int kPeakChains = 8;
+constexpr int kPeakUnroll = 16;
+__global__ void __launch_bounds__(256) gsf_dfma_peak_kernel(double *sink, int iters, double a, double b)
+{
+    double v[kPeakChains];
+#pragma unroll
+    for (int c = 0; c < kPeakChains; ++c) v[c] = (double)(threadIdx.x + c) * 1e-3;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < kPeakUnroll; ++u)
+#pragma unroll
+            for (int c = 0; c < kPeakChains; ++c) v[c] = fma(v[c], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int c = 0; c < kPeakChains; ++c) s += v[c];
+    if (s == 123.456) sink[0] = s;   // never true; keeps the chains alive
+}
+
+}  // namespace gsf

@@ -1,0 +1,953 @@
+// gsfield.cu -- C ABI (include/gsfield.h) and host runtime of the B200 field summation.
+//
+// Replaces the bodies of field::summator / summator_incompr / summator_fourier
+// (/root/reference/src/field.rs:37-65, 97-182, 219-249).  No CPU compute path exists here: every
+// entry point either runs the CUDA kernels of gsf_kernels.cuh or returns an error code.
+//
+// Host runtime in one paragraph: a process-wide context holds, per device, three pipeline slots
+// (stream + device chunk buffers + pinned staging).  Host-resident points are cut into chunks;
+// chunk c goes through slot c%3 as  [gather->pinned] -> H2D -> kernel -> D2H -> [scatter<-pinned]
+// so copies of neighbouring chunks overlap the kernel.  Pinned user memory skips the staging
+// steps, device-resident memory skips the copies.  With several devices configured the points are
+// sharded contiguously, one host thread per device, no collective.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/gsfield.h"
+#include "gsf_kernels.cuh"
+
+namespace {
+
+using gsf::kThreads;
+using gsf::SumArgs;
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define GSF_CUDA(call)                                                                     \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess)                                                             \
+            return fail(e_ == cudaErrorMemoryAllocation ? GSF_ERR_ALLOC : GSF_ERR_CUDA,    \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__,  \
+                        __LINE__);                                                         \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// kernel table
+typedef void (*SumKernel)(SumArgs);
+
+template <int D, int NC>
+SumKernel pick_pl(int P, int L)
+{
+#define GSF_V(p, l) \
+    if (P == p && L == l) return gsf::gsf_sum_kernel<D, NC, p, l>;
+    GSF_V(4, 1) GSF_V(2, 1) GSF_V(1, 1)
+    GSF_V(2, 2) GSF_V(2, 4) GSF_V(2, 8) GSF_V(2, 16) GSF_V(2, 32)
+    GSF_V(1, 2) GSF_V(1, 4) GSF_V(1, 8) GSF_V(1, 16) GSF_V(1, 32)
+#undef GSF_V
+    return nullptr;
+}
+
+template <int D>
+SumKernel pick_hi(int P, int L)   // dim 4..8: fewer variants
+{
+    if (P == 1 && L == 1) return gsf::gsf_sum_kernel<D, 1, 1, 1>;
+    if (P == 1 && L == 4) return gsf::gsf_sum_kernel<D, 1, 1, 4>;
+    if (P == 1 && L == 32) return gsf::gsf_sum_kernel<D, 1, 1, 32>;
+    return nullptr;
+}
+
+SumKernel pick_kernel(int dim, bool incompr, int P, int L)
+{
+    if (incompr) {
+        if (dim == 2) return pick_pl<2, 2>(P, L);
+        if (dim == 3) return pick_pl<3, 3>(P, L);
+        return nullptr;
+    }
+    switch (dim) {
+        case 1: return pick_pl<1, 1>(P, L);
+        case 2: return pick_pl<2, 1>(P, L);
+        case 3: return pick_pl<3, 1>(P, L);
+        case 4: return pick_hi<4>(P, L);
+        case 5: return pick_hi<5>(P, L);
+        case 6: return pick_hi<6>(P, L);
+        case 7: return pick_hi<7>(P, L);
+        case 8: return pick_hi<8>(P, L);
+    }
+    return nullptr;
+}
+
+// ---------------------------------------------------------------------------------------------
+constexpr int kSlots = 3;
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_h2d = nullptr;    // staging-in buffer consumed
+    cudaEvent_t ev_done = nullptr;   // D2H into staging-out finished
+    double *d_pos = nullptr, *d_out = nullptr;
+    double *h_pos = nullptr, *h_out = nullptr;
+    size_t d_pos_cap = 0, d_out_cap = 0, h_pos_cap = 0, h_out_cap = 0;   // in doubles
+};
+
+struct DeviceCtx {
+    int dev = -1;
+    int sm_count = 0;
+    bool ready = false;
+    Slot slot[kSlots];
+    cudaEvent_t ev_modes = nullptr;  // records are ready
+    cudaEvent_t ev_ws = nullptr;     // last consumer of the mode workspace
+    bool ws_used = false;
+    double *d_raw = nullptr, *d_rec = nullptr;
+    size_t raw_cap = 0, rec_cap = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof;   // pool of timing events
+    size_t prof_used = 0;
+    cudaEvent_t prep_beg = nullptr, prep_end = nullptr;
+    bool prep_timed = false;
+    // last-call bookkeeping
+    int64_t h2d_bytes = 0, d2h_bytes = 0;
+    int launches = 0, chunks = 0;
+    int status = GSF_OK;
+    std::string err;
+};
+
+struct Context {
+    std::mutex mu;
+    std::vector<int> devices;            // configured device ids
+    bool devices_explicit = false;
+    std::vector<DeviceCtx *> dctx;       // indexed by device id
+    int64_t chunk_points = 0;
+    int force_p = 0, force_l = 0;
+    bool profiling = false;
+    gsf_stats last{};
+    std::vector<int> last_devs;
+};
+
+Context &ctx()
+{
+    static Context c;
+    return c;
+}
+
+int device_count_raw()
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int ensure_cap(double **p, size_t *cap, size_t need, bool pinned)
+{
+    if (need == 0) need = 1;
+    if (*cap >= need) return GSF_OK;
+    if (*p) {
+        if (pinned) cudaFreeHost(*p); else cudaFree(*p);
+        *p = nullptr;
+        *cap = 0;
+    }
+    size_t want = need + need / 8;
+    cudaError_t e = pinned ? cudaMallocHost((void **)p, want * sizeof(double))
+                           : cudaMalloc((void **)p, want * sizeof(double));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(GSF_ERR_ALLOC, "%s of %zu bytes failed: %s", pinned ? "cudaMallocHost" : "cudaMalloc",
+                    want * sizeof(double), cudaGetErrorString(e));
+    }
+    *cap = want;
+    return GSF_OK;
+}
+
+int get_device_ctx(int dev, DeviceCtx **out)
+{
+    Context &c = ctx();
+    if (dev < 0) return fail(GSF_ERR_ARG, "bad device id %d", dev);
+    if ((size_t)dev >= c.dctx.size()) c.dctx.resize(dev + 1, nullptr);
+    if (!c.dctx[dev]) c.dctx[dev] = new DeviceCtx();
+    DeviceCtx *d = c.dctx[dev];
+    if (!d->ready) {
+        GSF_CUDA(cudaSetDevice(dev));
+        d->dev = dev;
+        cudaDeviceProp prop;
+        GSF_CUDA(cudaGetDeviceProperties(&prop, dev));
+        d->sm_count = prop.multiProcessorCount;
+        if (prop.major < 10)
+            return fail(GSF_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only",
+                        dev, prop.major, prop.minor);
+        for (int s = 0; s < kSlots; ++s) {
+            GSF_CUDA(cudaStreamCreateWithFlags(&d->slot[s].stream, cudaStreamNonBlocking));
+            GSF_CUDA(cudaEventCreateWithFlags(&d->slot[s].ev_h2d, cudaEventDisableTiming));
+            GSF_CUDA(cudaEventCreateWithFlags(&d->slot[s].ev_done, cudaEventDisableTiming));
+        }
+        GSF_CUDA(cudaEventCreateWithFlags(&d->ev_modes, cudaEventDisableTiming));
+        GSF_CUDA(cudaEventCreateWithFlags(&d->ev_ws, cudaEventDisableTiming));
+        GSF_CUDA(cudaEventCreate(&d->prep_beg));
+        GSF_CUDA(cudaEventCreate(&d->prep_end));
+        d->ready = true;
+    }
+    *out = d;
+    return GSF_OK;
+}
+
+void free_device_ctx(DeviceCtx *d)
+{
+    if (!d) return;
+    if (d->ready) {
+        cudaSetDevice(d->dev);
+        cudaDeviceSynchronize();
+        for (int s = 0; s < kSlots; ++s) {
+            Slot &sl = d->slot[s];
+            if (sl.d_pos) cudaFree(sl.d_pos);
+            if (sl.d_out) cudaFree(sl.d_out);
+            if (sl.h_pos) cudaFreeHost(sl.h_pos);
+            if (sl.h_out) cudaFreeHost(sl.h_out);
+            if (sl.ev_h2d) cudaEventDestroy(sl.ev_h2d);
+            if (sl.ev_done) cudaEventDestroy(sl.ev_done);
+            if (sl.stream) cudaStreamDestroy(sl.stream);
+        }
+        if (d->d_raw) cudaFree(d->d_raw);
+        if (d->d_rec) cudaFree(d->d_rec);
+        for (auto &pr : d->prof) {
+            cudaEventDestroy(pr.first);
+            cudaEventDestroy(pr.second);
+        }
+        cudaEventDestroy(d->ev_modes);
+        cudaEventDestroy(d->ev_ws);
+        cudaEventDestroy(d->prep_beg);
+        cudaEventDestroy(d->prep_end);
+    }
+    delete d;
+}
+
+// memory kind of a user pointer: 0 pageable host, 1 pinned host, 2 device/managed
+int classify(const void *p, int *kind, int *device)
+{
+    cudaPointerAttributes at;
+    cudaError_t e = cudaPointerGetAttributes(&at, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *kind = 0;
+        *device = -1;
+        return GSF_OK;
+    }
+    switch (at.type) {
+        case cudaMemoryTypeHost: *kind = 1; *device = -1; break;
+        case cudaMemoryTypeDevice:
+        case cudaMemoryTypeManaged: *kind = 2; *device = at.device; break;
+        default: *kind = 0; *device = -1; break;
+    }
+    return GSF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+struct Problem {
+    int kind;            // gsf::Kind
+    int dim;
+    int64_t N, M;
+    const double *sf; int64_t sfs;
+    const double *k;  int64_t ks0, ks1;
+    const double *z1; int64_t z1s;
+    const double *z2; int64_t z2s;
+    const double *pos; int64_t ps0, ps1;
+    double *out; int64_t os0, os1;
+    int nc() const { return kind == gsf::kIncompr ? dim : 1; }
+    int rec() const { return gsf::rec_doubles(dim, nc()); }
+};
+
+int validate(const Problem &p)
+{
+    if (p.N < 0 || p.M < 0) return fail(GSF_ERR_SHAPE, "negative size: n_modes=%lld n_points=%lld",
+                                        (long long)p.N, (long long)p.M);
+    if (p.kind == gsf::kIncompr) {
+        if (p.dim != 2 && p.dim != 3)
+            return fail(GSF_ERR_DIM, "Only two- and three-dimensional problems are supported. (dim=%d)", p.dim);
+        if (p.N == 0) return fail(GSF_ERR_EMPTY_MODES, "summate_incompr needs at least one mode");
+    } else if (p.dim < 1 || p.dim > GSF_MAX_DIM) {
+        return fail(GSF_ERR_DIM, "dim=%d outside the supported range 1..%d", p.dim, GSF_MAX_DIM);
+    }
+    if (p.N > 0 && (!p.k || !p.z1 || !p.z2 || (p.kind == gsf::kFourier && !p.sf)))
+        return fail(GSF_ERR_ARG, "NULL mode array");
+    if (p.M > 0 && (!p.pos || !p.out)) return fail(GSF_ERR_ARG, "NULL pos/out");
+    return GSF_OK;
+}
+
+// choose points-per-thread P and lanes-per-point L so the grid fills the machine
+void choose_variant(const DeviceCtx &d, const Problem &p, int64_t m_launch, int *P, int *L)
+{
+    Context &c = ctx();
+    const bool hi_dim = p.dim > 3;
+    if (c.force_p > 0 && c.force_l > 0 && pick_kernel(p.dim, p.kind == gsf::kIncompr, c.force_p, c.force_l)) {
+        *P = c.force_p;
+        *L = c.force_l;
+        return;
+    }
+    const int cand_l_lo[] = {1, 2, 4, 8, 16, 32};
+    const int cand_l_hi[] = {1, 4, 32};
+    const int *cl = hi_dim ? cand_l_hi : cand_l_lo;
+    const int ncl = hi_dim ? 3 : 6;
+    const int p0 = hi_dim ? 1 : 2;
+    const double slots = (double)d.sm_count * 4.0;   // ~4 resident CTAs of 128 threads per SM
+    int bestP = p0, bestL = 1;
+    double best = -1.0;
+    for (int li = 0; li < ncl; ++li) {
+        const int l = cl[li];
+        if (l > 1 && p.N / l < 8 && li > 0) break;   // keep >= 8 modes per lane
+        const double ctas = (double)((m_launch * l + (int64_t)p0 * kThreads - 1) / ((int64_t)p0 * kThreads));
+        const double w = ctas / slots;
+        const double eff = w >= 1.0 ? w / (double)(int64_t)(w + 0.999999) : w;
+        const double score = eff - 0.01 * li;        // prefer small L on ties
+        if (score > best) {
+            best = score;
+            bestP = p0;
+            bestL = l;
+        }
+        if (eff >= 0.96) break;
+    }
+    *P = bestP;
+    *L = bestL;
+}
+
+int launch_sum(DeviceCtx &d, const Problem &p, const double *kpos, int64_t ps0, int64_t ps1, double *kout,
+               int64_t os0, int64_t os1, int64_t m, cudaStream_t st, int P, int L)
+{
+    SumKernel fn = pick_kernel(p.dim, p.kind == gsf::kIncompr, P, L);
+    if (!fn) return fail(GSF_ERR_ARG, "no kernel variant dim=%d P=%d L=%d", p.dim, P, L);
+    SumArgs a;
+    a.rec = d.d_rec;
+    a.n_modes = p.N;
+    a.pos = kpos; a.ps0 = ps0; a.ps1 = ps1;
+    a.n_points = m;
+    a.out = kout; a.os0 = os0; a.os1 = os1;
+    const int64_t tile = (int64_t)P * (kThreads / L);
+    const int64_t grid = (m + tile - 1) / tile;
+    if (grid > 0x7fffffffLL) return fail(GSF_ERR_SHAPE, "chunk of %lld points is too large for one launch", (long long)m);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (ctx().profiling) {
+        if (d.prof_used == d.prof.size()) {
+            cudaEvent_t a0, a1;
+            GSF_CUDA(cudaEventCreate(&a0));
+            GSF_CUDA(cudaEventCreate(&a1));
+            d.prof.emplace_back(a0, a1);
+        }
+        e0 = d.prof[d.prof_used].first;
+        e1 = d.prof[d.prof_used].second;
+        d.prof_used++;
+        GSF_CUDA(cudaEventRecord(e0, st));
+    }
+    fn<<<(unsigned)grid, kThreads, 0, st>>>(a);
+    GSF_CUDA(cudaGetLastError());
+    if (e1) GSF_CUDA(cudaEventRecord(e1, st));
+    d.launches++;
+    return GSF_OK;
+}
+
+// Upload (if host) and pre-process the modes on `st`.  Host arrays are gathered into a contiguous
+// temporary and copied with a pageable cudaMemcpyAsync (staged by the driver before it returns).
+int prepare_modes(DeviceCtx &d, const Problem &p, cudaStream_t st)
+{
+    const int64_t N = p.N;
+    int rc;
+    if ((rc = ensure_cap(&d.d_rec, &d.rec_cap, (size_t)N * p.rec(), false))) return rc;
+    if (N == 0) return GSF_OK;
+    int kk, kd, tmp;
+    classify(p.k, &kk, &kd);
+    int k1, k2, k3 = kk;
+    classify(p.z1, &k1, &tmp);
+    classify(p.z2, &k2, &tmp);
+    if (p.kind == gsf::kFourier) classify(p.sf, &k3, &tmp);
+    const bool all_dev = kk == 2 && k1 == 2 && k2 == 2 && k3 == 2;
+    const bool all_host = kk != 2 && k1 != 2 && k2 != 2 && k3 != 2;
+    if (!all_dev && !all_host)
+        return fail(GSF_ERR_ARG, "mode arrays must be all host-resident or all device-resident");
+
+    gsf::PrepArgs a;
+    a.n_modes = N;
+    a.dim = p.dim;
+    a.incompr = p.kind == gsf::kIncompr;
+    a.rec = d.d_rec;
+    if (all_dev) {
+        if (kd != d.dev) return fail(GSF_ERR_ARG, "mode arrays live on device %d, work runs on device %d", kd, d.dev);
+        a.k = p.k; a.ks0 = p.ks0; a.ks1 = p.ks1;
+        a.z1 = p.z1; a.z1s = p.z1s;
+        a.z2 = p.z2; a.z2s = p.z2s;
+        a.sf = p.kind == gsf::kFourier ? p.sf : nullptr; a.sfs = p.sfs;
+    } else {
+        const int rows = p.dim + 2 + (p.kind == gsf::kFourier ? 1 : 0);
+        if ((rc = ensure_cap(&d.d_raw, &d.raw_cap, (size_t)rows * N, false))) return rc;
+        std::vector<double> h((size_t)rows * N);
+        for (int dd = 0; dd < p.dim; ++dd)
+            for (int64_t i = 0; i < N; ++i) h[(size_t)dd * N + i] = p.k[dd * p.ks0 + i * p.ks1];
+        for (int64_t i = 0; i < N; ++i) h[(size_t)p.dim * N + i] = p.z1[i * p.z1s];
+        for (int64_t i = 0; i < N; ++i) h[(size_t)(p.dim + 1) * N + i] = p.z2[i * p.z2s];
+        if (p.kind == gsf::kFourier)
+            for (int64_t i = 0; i < N; ++i) h[(size_t)(p.dim + 2) * N + i] = p.sf[i * p.sfs];
+        GSF_CUDA(cudaMemcpyAsync(d.d_raw, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+        d.h2d_bytes += (int64_t)(h.size() * sizeof(double));
+        a.k = d.d_raw; a.ks0 = N; a.ks1 = 1;
+        a.z1 = d.d_raw + (size_t)p.dim * N; a.z1s = 1;
+        a.z2 = d.d_raw + (size_t)(p.dim + 1) * N; a.z2s = 1;
+        a.sf = p.kind == gsf::kFourier ? d.d_raw + (size_t)(p.dim + 2) * N : nullptr; a.sfs = 1;
+    }
+    d.prep_timed = ctx().profiling;
+    if (d.prep_timed) GSF_CUDA(cudaEventRecord(d.prep_beg, st));
+    gsf::gsf_prep_modes<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(a);
+    GSF_CUDA(cudaGetLastError());
+    if (d.prep_timed) GSF_CUDA(cudaEventRecord(d.prep_end, st));
+    d.launches++;
+    return GSF_OK;
+}
+
+void reset_call_counters(DeviceCtx &d)
+{
+    d.h2d_bytes = d.d2h_bytes = 0;
+    d.launches = d.chunks = 0;
+    d.prof_used = 0;
+    d.prep_timed = false;
+    d.status = GSF_OK;
+    d.err.clear();
+}
+
+// gather rows [j0, j0+cnt) of a strided (dim, M) host array into `dst` (row stride cnt)
+void gather_pos(const Problem &p, int64_t j0, int64_t cnt, double *dst)
+{
+    for (int a = 0; a < p.dim; ++a) {
+        const double *src = p.pos + a * p.ps0 + j0 * p.ps1;
+        double *row = dst + (size_t)a * cnt;
+        if (p.ps1 == 1) {
+            memcpy(row, src, (size_t)cnt * sizeof(double));
+        } else {
+            for (int64_t j = 0; j < cnt; ++j) row[j] = src[j * p.ps1];
+        }
+    }
+}
+
+struct OutLayout {
+    bool aos;           // device chunk is cnt records of nc doubles (else nc rows of cnt)
+    bool direct;        // D2H straight into the user's buffer
+};
+
+// scatter a finished staging-out chunk into the user's (strided) output
+void scatter_out(const Problem &p, const OutLayout &lay, int64_t j0, int64_t cnt, const double *src)
+{
+    const int nc = p.nc();
+    if (nc == 1) {
+        if (p.os1 == 1) {
+            memcpy(p.out + j0, src, (size_t)cnt * sizeof(double));
+        } else {
+            for (int64_t j = 0; j < cnt; ++j) p.out[(j0 + j) * p.os1] = src[j];
+        }
+        return;
+    }
+    if (lay.aos) {   // os0 == 1, os1 == nc: contiguous records
+        memcpy(p.out + j0 * p.os1, src, (size_t)cnt * nc * sizeof(double));
+        return;
+    }
+    for (int a = 0; a < nc; ++a) {
+        const double *row = src + (size_t)a * cnt;
+        double *dst = p.out + a * p.os0 + j0 * p.os1;
+        if (p.os1 == 1) {
+            memcpy(dst, row, (size_t)cnt * sizeof(double));
+        } else {
+            for (int64_t j = 0; j < cnt; ++j) dst[j * p.os1] = row[j];
+        }
+    }
+}
+
+// Process points [j_beg, j_end) of the problem on device d (host- or device-resident pos/out).
+int run_shard(DeviceCtx &d, const Problem &p, int64_t j_beg, int64_t j_end, int pos_kind, int out_kind,
+              int *P_used, int *L_used)
+{
+    GSF_CUDA(cudaSetDevice(d.dev));
+    reset_call_counters(d);
+    const int nc = p.nc();
+    const int64_t m_shard = j_end - j_beg;
+    int rc;
+
+    cudaStream_t s0 = d.slot[0].stream;
+    if (d.ws_used) GSF_CUDA(cudaStreamWaitEvent(s0, d.ev_ws, 0));
+    if ((rc = prepare_modes(d, p, s0))) return rc;
+    GSF_CUDA(cudaEventRecord(d.ev_modes, s0));
+    for (int s = 1; s < kSlots; ++s) GSF_CUDA(cudaStreamWaitEvent(d.slot[s].stream, d.ev_modes, 0));
+
+    const bool pos_dev = pos_kind == 2, out_dev = out_kind == 2;
+    // chunking: device-resident both ways => one launch; otherwise pipeline chunks
+    int64_t chunk = m_shard;
+    if (!(pos_dev && out_dev)) {
+        chunk = ctx().chunk_points;
+        if (chunk <= 0) {
+            chunk = (m_shard + 7) / 8;
+            chunk = std::max<int64_t>(chunk, 1 << 15);
+            chunk = std::min<int64_t>(chunk, 1 << 20);
+        }
+        chunk = (chunk + 1023) / 1024 * 1024;
+        chunk = std::min(chunk, std::max<int64_t>(m_shard, 1));
+    }
+    const int64_t n_chunks = m_shard > 0 ? (m_shard + chunk - 1) / chunk : 0;
+
+    const bool direct_in = pos_kind == 1 && p.ps1 == 1;
+    OutLayout lay;
+    lay.aos = nc > 1 && p.os0 == 1 && p.os1 == nc;
+    lay.direct = out_kind == 1 && (nc == 1 ? p.os1 == 1 : (lay.aos || p.os1 == 1));
+
+    int P = 2, L = 1;
+    choose_variant(d, p, std::min(chunk, m_shard), &P, &L);
+    *P_used = P;
+    *L_used = L;
+
+    struct Pending { int64_t j0, cnt; bool live; } pend[kSlots] = {};
+    bool slot_in_used[kSlots] = {false, false, false};
+
+    for (int64_t c = 0; c < n_chunks; ++c) {
+        const int si = (int)(c % kSlots);
+        Slot &sl = d.slot[si];
+        cudaStream_t st = sl.stream;
+        const int64_t j0 = j_beg + c * chunk;
+        const int64_t cnt = std::min(chunk, j_end - j0);
+
+        // drain the staging-out buffer of the chunk that used this slot last
+        if (pend[si].live) {
+            GSF_CUDA(cudaEventSynchronize(sl.ev_done));
+            scatter_out(p, lay, pend[si].j0, pend[si].cnt, sl.h_out);
+            pend[si].live = false;
+        }
+
+        // ---- input
+        const double *kpos;
+        int64_t kps0, kps1;
+        if (pos_dev) {
+            kpos = p.pos + j0 * p.ps1;
+            kps0 = p.ps0;
+            kps1 = p.ps1;
+        } else {
+            if ((rc = ensure_cap(&sl.d_pos, &sl.d_pos_cap, (size_t)p.dim * cnt, false))) return rc;
+            if (direct_in) {
+                for (int a = 0; a < p.dim; ++a)
+                    GSF_CUDA(cudaMemcpyAsync(sl.d_pos + (size_t)a * cnt, p.pos + a * p.ps0 + j0,
+                                             (size_t)cnt * sizeof(double), cudaMemcpyHostToDevice, st));
+            } else {
+                if ((rc = ensure_cap(&sl.h_pos, &sl.h_pos_cap, (size_t)p.dim * cnt, true))) return rc;
+                if (slot_in_used[si]) GSF_CUDA(cudaEventSynchronize(sl.ev_h2d));
+                gather_pos(p, j0, cnt, sl.h_pos);
+                GSF_CUDA(cudaMemcpyAsync(sl.d_pos, sl.h_pos, (size_t)p.dim * cnt * sizeof(double),
+                                         cudaMemcpyHostToDevice, st));
+                GSF_CUDA(cudaEventRecord(sl.ev_h2d, st));
+                slot_in_used[si] = true;
+            }
+            d.h2d_bytes += (int64_t)p.dim * cnt * (int64_t)sizeof(double);
+            kpos = sl.d_pos;
+            kps0 = cnt;
+            kps1 = 1;
+        }
+
+        // ---- kernel
+        double *kout;
+        int64_t kos0, kos1;
+        if (out_dev) {
+            kout = p.out + j0 * p.os1;
+            kos0 = p.os0;
+            kos1 = p.os1;
+        } else {
+            if ((rc = ensure_cap(&sl.d_out, &sl.d_out_cap, (size_t)nc * cnt, false))) return rc;
+            kout = sl.d_out;
+            if (lay.aos) { kos0 = 1; kos1 = nc; } else { kos0 = cnt; kos1 = 1; }
+        }
+        if ((rc = launch_sum(d, p, kpos, kps0, kps1, kout, kos0, kos1, cnt, st, P, L))) return rc;
+
+        // ---- output
+        if (!out_dev) {
+            if (lay.direct) {
+                if (nc == 1 || lay.aos) {
+                    GSF_CUDA(cudaMemcpyAsync(p.out + j0 * p.os1, sl.d_out, (size_t)nc * cnt * sizeof(double),
+                                             cudaMemcpyDeviceToHost, st));
+                } else {
+                    for (int a = 0; a < nc; ++a)
+                        GSF_CUDA(cudaMemcpyAsync(p.out + a * p.os0 + j0, sl.d_out + (size_t)a * cnt,
+                                                 (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, st));
+                }
+            } else {
+                if ((rc = ensure_cap(&sl.h_out, &sl.h_out_cap, (size_t)nc * cnt, true))) return rc;
+                GSF_CUDA(cudaMemcpyAsync(sl.h_out, sl.d_out, (size_t)nc * cnt * sizeof(double),
+                                         cudaMemcpyDeviceToHost, st));
+                GSF_CUDA(cudaEventRecord(sl.ev_done, st));
+                pend[si] = {j0, cnt, true};
+            }
+            d.d2h_bytes += (int64_t)nc * cnt * (int64_t)sizeof(double);
+        }
+        d.chunks++;
+    }
+
+    // drain in issue order
+    for (int64_t c = std::max<int64_t>(0, n_chunks - kSlots); c < n_chunks; ++c) {
+        const int si = (int)(c % kSlots);
+        if (pend[si].live) {
+            GSF_CUDA(cudaEventSynchronize(d.slot[si].ev_done));
+            scatter_out(p, lay, pend[si].j0, pend[si].cnt, d.slot[si].h_out);
+            pend[si].live = false;
+        }
+    }
+    for (int s = 0; s < kSlots; ++s) GSF_CUDA(cudaStreamSynchronize(d.slot[s].stream));
+    d.ws_used = false;   // everything that read the workspace has finished
+    return GSF_OK;
+}
+
+std::vector<int> default_devices()
+{
+    std::vector<int> v;
+    const char *e = getenv("GSF_DEVICES");
+    if (e && *e) {
+        const char *s = e;
+        while (*s) {
+            char *end;
+            long id = strtol(s, &end, 10);
+            if (end == s) break;
+            v.push_back((int)id);
+            s = *end == ',' ? end + 1 : end;
+        }
+    }
+    if (v.empty()) v.push_back(0);
+    return v;
+}
+
+void collect_stats(const Problem &p, const std::vector<DeviceCtx *> &used, double total_ms, int P, int L,
+                   int pos_kind, int out_kind)
+{
+    Context &c = ctx();
+    gsf_stats s{};
+    s.total_ms = total_ms;
+    s.point_modes = p.N * p.M;
+    s.points_per_thread = P;
+    s.lanes_per_point = L;
+    s.pos_memory = pos_kind;
+    s.out_memory = out_kind;
+    s.n_devices = (int)used.size();
+    c.last_devs.clear();
+    for (DeviceCtx *d : used) {
+        s.h2d_bytes += d->h2d_bytes;
+        s.d2h_bytes += d->d2h_bytes;
+        s.kernel_launches += d->launches;
+        s.n_chunks += d->chunks;
+        c.last_devs.push_back(d->dev);
+    }
+    s.kernel_ms = -1.0;   // resolved lazily in gsf_get_last_stats (needs event sync)
+    s.prep_ms = -1.0;
+    c.last = s;
+}
+
+int run_host_call(const Problem &p)
+{
+    Context &c = ctx();
+    std::lock_guard<std::mutex> lock(c.mu);
+    int rc = validate(p);
+    if (rc) return rc;
+    const int ndev_visible = device_count_raw();
+    if (ndev_visible <= 0)
+        return fail(GSF_ERR_NO_DEVICE, "no CUDA device available; gsfield has no CPU path");
+    if (p.M == 0) {
+        c.last = gsf_stats{};
+        return GSF_OK;
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+
+    int pos_kind, pos_dev, out_kind, out_dev;
+    classify(p.pos, &pos_kind, &pos_dev);
+    classify(p.out, &out_kind, &out_dev);
+
+    std::vector<int> devs = c.devices_explicit ? c.devices : default_devices();
+    for (int id : devs)
+        if (id < 0 || id >= ndev_visible) return fail(GSF_ERR_ARG, "configured device %d not visible (%d devices)", id, ndev_visible);
+    if (pos_kind == 2 || out_kind == 2) {
+        // device-resident data pins the work to that device
+        const int dv = pos_kind == 2 ? pos_dev : out_dev;
+        if (pos_kind == 2 && out_kind == 2 && pos_dev != out_dev)
+            return fail(GSF_ERR_ARG, "pos on device %d but out on device %d", pos_dev, out_dev);
+        devs.assign(1, dv);
+    }
+    // do not spread tiny problems: at least 2^16 points per device
+    int G = (int)devs.size();
+    G = (int)std::max<int64_t>(1, std::min<int64_t>(G, p.M / 65536));
+    devs.resize(G);
+
+    std::vector<DeviceCtx *> used(G);
+    for (int g = 0; g < G; ++g)
+        if ((rc = get_device_ctx(devs[g], &used[g]))) return rc;
+
+    int P = 0, L = 0;
+    if (G == 1) {
+        rc = run_shard(*used[0], p, 0, p.M, pos_kind, out_kind, &P, &L);
+    } else {
+        std::vector<std::thread> th;
+        std::vector<int> Ps(G), Ls(G);
+        for (int g = 0; g < G; ++g) {
+            const int64_t j0 = p.M * g / G / 1024 * 1024;
+            const int64_t j1 = g + 1 == G ? p.M : p.M * (g + 1) / G / 1024 * 1024;
+            th.emplace_back([&, g, j0, j1]() {
+                DeviceCtx &d = *used[g];
+                int r = run_shard(d, p, j0, j1, pos_kind, out_kind, &Ps[g], &Ls[g]);
+                d.status = r;
+                if (r) d.err = g_err;   // g_err is thread-local to the worker
+            });
+        }
+        for (auto &t : th) t.join();
+        for (int g = 0; g < G; ++g)
+            if (used[g]->status && !rc) {
+                rc = used[g]->status;
+                g_err = used[g]->err;
+            }
+        P = Ps[0];
+        L = Ls[0];
+    }
+    if (rc) return rc;
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    collect_stats(p, used, ms, P, L, pos_kind, out_kind);
+    return GSF_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+int gsf_abi_version(void) { return GSF_ABI_VERSION; }
+
+int gsf_device_count(void) { return device_count_raw(); }
+
+const char *gsf_last_error(void) { return g_err.c_str(); }
+
+int gsf_summate(int dim, int64_t n_modes, int64_t n_points, const double *cov_samples, int64_t cov_s0,
+                int64_t cov_s1, const double *z1, int64_t z1_s, const double *z2, int64_t z2_s,
+                const double *pos, int64_t pos_s0, int64_t pos_s1, double *out, int num_threads)
+{
+    (void)num_threads;
+    Problem p{gsf::kScalar, dim, n_modes, n_points, nullptr, 0, cov_samples, cov_s0, cov_s1, z1, z1_s,
+              z2, z2_s, pos, pos_s0, pos_s1, out, 0, 1};
+    return run_host_call(p);
+}
+
+int gsf_summate_incompr(int dim, int64_t n_modes, int64_t n_points, const double *cov_samples,
+                        int64_t cov_s0, int64_t cov_s1, const double *z1, int64_t z1_s, const double *z2,
+                        int64_t z2_s, const double *pos, int64_t pos_s0, int64_t pos_s1, double *out,
+                        int64_t out_s0, int64_t out_s1, int num_threads)
+{
+    (void)num_threads;
+    Problem p{gsf::kIncompr, dim, n_modes, n_points, nullptr, 0, cov_samples, cov_s0, cov_s1, z1, z1_s,
+              z2, z2_s, pos, pos_s0, pos_s1, out, out_s0, out_s1};
+    return run_host_call(p);
+}
+
+int gsf_summate_fourier(int dim, int64_t n_modes, int64_t n_points, const double *spectrum_factor,
+                        int64_t sf_s, const double *modes, int64_t modes_s0, int64_t modes_s1,
+                        const double *z1, int64_t z1_s, const double *z2, int64_t z2_s, const double *pos,
+                        int64_t pos_s0, int64_t pos_s1, double *out, int num_threads)
+{
+    (void)num_threads;
+    Problem p{gsf::kFourier, dim, n_modes, n_points, spectrum_factor, sf_s, modes, modes_s0, modes_s1,
+              z1, z1_s, z2, z2_s, pos, pos_s0, pos_s1, out, 0, 1};
+    return run_host_call(p);
+}
+
+int gsf_summate_on_stream(int kind, int dim, int64_t n_modes, int64_t n_points, const double *spectrum_factor,
+                          int64_t sf_s, const double *cov_samples, int64_t cov_s0, int64_t cov_s1,
+                          const double *z1, int64_t z1_s, const double *z2, int64_t z2_s, const double *pos,
+                          int64_t pos_s0, int64_t pos_s1, double *out, int64_t out_s0, int64_t out_s1,
+                          void *cuda_stream)
+{
+    if (kind < 0 || kind > 2) return fail(GSF_ERR_ARG, "kind must be 0, 1 or 2");
+    Problem p{kind, dim, n_modes, n_points, spectrum_factor, sf_s, cov_samples, cov_s0, cov_s1, z1, z1_s,
+              z2, z2_s, pos, pos_s0, pos_s1, out, out_s0, out_s1};
+    if (kind != gsf::kIncompr) { p.os0 = 0; p.os1 = 1; }
+    Context &c = ctx();
+    std::lock_guard<std::mutex> lock(c.mu);
+    int rc = validate(p);
+    if (rc) return rc;
+    if (device_count_raw() <= 0)
+        return fail(GSF_ERR_NO_DEVICE, "no CUDA device available; gsfield has no CPU path");
+    if (p.M == 0) return GSF_OK;
+    int pk, pd, ok, od;
+    classify(p.pos, &pk, &pd);
+    classify(p.out, &ok, &od);
+    if (pk != 2 || ok != 2 || pd != od)
+        return fail(GSF_ERR_ARG, "gsf_summate_on_stream needs pos and out in device memory of one device");
+    DeviceCtx *d;
+    if ((rc = get_device_ctx(pd, &d))) return rc;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    GSF_CUDA(cudaSetDevice(pd));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    reset_call_counters(*d);
+    const auto t0 = std::chrono::steady_clock::now();
+    if (d->ws_used) GSF_CUDA(cudaStreamWaitEvent(st, d->ev_ws, 0));
+    if ((rc = prepare_modes(*d, p, st))) return rc;
+    int P, L;
+    choose_variant(*d, p, p.M, &P, &L);
+    if ((rc = launch_sum(*d, p, p.pos, p.ps0, p.ps1, p.out, p.os0, p.os1, p.M, st, P, L))) return rc;
+    GSF_CUDA(cudaEventRecord(d->ev_ws, st));
+    d->ws_used = true;
+    d->chunks = 1;
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    std::vector<DeviceCtx *> used(1, d);
+    collect_stats(p, used, ms, P, L, 2, 2);
+    if (prev != pd) cudaSetDevice(prev);
+    return GSF_OK;
+}
+
+int gsf_set_devices(const int *device_ids, int n)
+{
+    Context &c = ctx();
+    std::lock_guard<std::mutex> lock(c.mu);
+    if (n <= 0 || !device_ids) {
+        c.devices.clear();
+        c.devices_explicit = false;
+        return GSF_OK;
+    }
+    const int vis = device_count_raw();
+    for (int i = 0; i < n; ++i)
+        if (device_ids[i] < 0 || device_ids[i] >= vis)
+            return fail(GSF_ERR_ARG, "device %d not visible (%d devices)", device_ids[i], vis);
+    c.devices.assign(device_ids, device_ids + n);
+    c.devices_explicit = true;
+    return GSF_OK;
+}
+
+int gsf_set_chunk_points(int64_t chunk_points)
+{
+    Context &c = ctx();
+    std::lock_guard<std::mutex> lock(c.mu);
+    if (chunk_points < 0) return fail(GSF_ERR_ARG, "chunk_points < 0");
+    c.chunk_points = chunk_points;
+    return GSF_OK;
+}
+
+int gsf_set_variant(int points_per_thread, int lanes_per_point)
+{
+    Context &c = ctx();
+    std::lock_guard<std::mutex> lock(c.mu);
+    if (points_per_thread == 0 && lanes_per_point == 0) {
+        c.force_p = c.force_l = 0;
+        return GSF_OK;
+    }
+    if (!pick_kernel(3, false, points_per_thread, lanes_per_point))
+        return fail(GSF_ERR_ARG, "no kernel variant P=%d L=%d", points_per_thread, lanes_per_point);
+    c.force_p = points_per_thread;
+    c.force_l = lanes_per_point;
+    return GSF_OK;
+}
+
+int gsf_set_profiling(int enabled)
+{
+    Context &c = ctx();
+    std::lock_guard<std::mutex> lock(c.mu);
+    c.profiling = enabled != 0;
+    return GSF_OK;
+}
+
+int gsf_get_last_stats(gsf_stats *out)
+{
+    if (!out) return fail(GSF_ERR_ARG, "NULL stats");
+    Context &c = ctx();
+    std::lock_guard<std::mutex> lock(c.mu);
+    gsf_stats s = c.last;
+    double kmax = -1.0, pmax = -1.0;
+    for (int dev : c.last_devs) {
+        DeviceCtx *d = c.dctx[dev];
+        if (!d || d->prof_used == 0) continue;
+        cudaSetDevice(dev);
+        double sum = 0.0;
+        for (size_t i = 0; i < d->prof_used; ++i) {
+            float ms = 0.f;
+            if (cudaEventSynchronize(d->prof[i].second) != cudaSuccess ||
+                cudaEventElapsedTime(&ms, d->prof[i].first, d->prof[i].second) != cudaSuccess) {
+                cudaGetLastError();
+                sum = -1.0;
+                break;
+            }
+            sum += ms;
+        }
+        kmax = std::max(kmax, sum);
+        if (d->prep_timed) {
+            float ms = 0.f;
+            if (cudaEventSynchronize(d->prep_end) == cudaSuccess &&
+                cudaEventElapsedTime(&ms, d->prep_beg, d->prep_end) == cudaSuccess)
+                pmax = std::max(pmax, (double)ms);
+            else
+                cudaGetLastError();
+        }
+    }
+    s.kernel_ms = kmax;
+    s.prep_ms = pmax;
+    *out = s;
+    return GSF_OK;
+}
+
+int gsf_shutdown(void)
+{
+    Context &c = ctx();
+    std::lock_guard<std::mutex> lock(c.mu);
+    for (DeviceCtx *d : c.dctx) free_device_ctx(d);
+    c.dctx.clear();
+    c.last = gsf_stats{};
+    c.last_devs.clear();
+    return GSF_OK;
+}
+
+int gsf_dfma_peak(int device, double min_ms, double *dfma_per_s, double *elapsed_ms)
+{
+    Context &c = ctx();
+    std::lock_guard<std::mutex> lock(c.mu);
+    if (device_count_raw() <= 0) return fail(GSF_ERR_NO_DEVICE, "no CUDA device available");
+    DeviceCtx *d;
+    int rc = get_device_ctx(device, &d);
+    if (rc) return rc;
+    GSF_CUDA(cudaSetDevice(device));
+    double *sink;
+    GSF_CUDA(cudaMalloc((void **)&sink, sizeof(double)));
+    cudaEvent_t e0, e1;
+    GSF_CUDA(cudaEventCreate(&e0));
+    GSF_CUDA(cudaEventCreate(&e1));
+    const int threads = 256;
+    const int blocks = d->sm_count * 8;   // 2048 threads per SM
+    cudaStream_t st = d->slot[0].stream;
+    int iters = 2000;
+    float ms = 0.f;
+    for (int attempt = 0; attempt < 12; ++attempt) {
+        GSF_CUDA(cudaEventRecord(e0, st));
+        gsf::gsf_dfma_peak_kernel<<<blocks, threads, 0, st>>>(sink, iters, 0.999999, 1e-9);
+        GSF_CUDA(cudaGetLastError());
+        GSF_CUDA(cudaEventRecord(e1, st));
+        GSF_CUDA(cudaEventSynchronize(e1));
+        GSF_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms >= min_ms || iters > (1 << 28)) break;
+        const double scale = ms > 0.05 ? std::min(16.0, 1.25 * min_ms / ms) : 16.0;
+        iters = (int)std::min<double>((double)iters * std::max(scale, 1.5), 1 << 29);
+    }
+    const double n = (double)blocks * threads * (double)iters * gsf::kPeakChains * gsf::kPeakUnroll;
+    if (dfma_per_s) *dfma_per_s = n / (ms * 1e-3);
+    if (elapsed_ms) *elapsed_ms = ms;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    return GSF_OK;
+}
+
+}  // extern "C"

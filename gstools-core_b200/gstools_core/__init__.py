@@ -1,0 +1,314 @@
+"""gstools_core -- B200-native drop-in for the field-summation part of GSTools-Core's pyo3 module.
+
+Mirrors the three Python functions GSTools imports from the reference's `gstools_core`
+(/root/reference/src/lib.rs:33-84): same names, same positional order, same return shapes
+
+    summate(cov_samples, z1, z2, pos, num_threads=None)                 -> ndarray (M,)
+    summate_incompr(cov_samples, z1, z2, pos, num_threads=None)         -> ndarray (d, M), F-ordered
+    summate_fourier(spectrum_factor, modes, z1, z2, pos, num_threads=None) -> ndarray (M,)
+
+but the work is done by hand-written sm_100a CUDA kernels behind the C ABI in include/gsfield.h
+(libgsfield.so, built in-tree by csrc/Makefile).  There is no CPU fallback: if the library is
+missing or no CUDA device is usable the call raises.
+
+Differences from the reference, all deliberate:
+  * a shape / dim mismatch raises ValueError instead of aborting the process (the reference
+    panics with panic="abort", Cargo.toml:22);
+  * `pos` (and the mode arrays) may also be objects exposing ``__cuda_array_interface__``
+    (e.g. torch CUDA tensors); the result is then returned in device memory as the same kind of
+    object via the ``out=`` argument of the ``*_device`` helpers.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+__version__ = "1.1.0+b200.0"   # reference crate version (Cargo.toml:3) + local build tag
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libgsfield.so")
+
+_i64 = ctypes.c_int64
+_vp = ctypes.c_void_p
+_int = ctypes.c_int
+
+
+class GsfStats(ctypes.Structure):
+    _fields_ = [
+        ("total_ms", ctypes.c_double), ("kernel_ms", ctypes.c_double), ("prep_ms", ctypes.c_double),
+        ("point_modes", _i64), ("h2d_bytes", _i64), ("d2h_bytes", _i64),
+        ("kernel_launches", ctypes.c_int32), ("n_devices", ctypes.c_int32), ("n_chunks", ctypes.c_int32),
+        ("points_per_thread", ctypes.c_int32), ("lanes_per_point", ctypes.c_int32),
+        ("pos_memory", ctypes.c_int32), ("out_memory", ctypes.c_int32), ("reserved", ctypes.c_int32),
+    ]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
+
+
+_lib = None
+
+
+def _load():
+    """Load libgsfield.so; fail loudly (no fallback) if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise ImportError(
+            "gstools_core (B200): %s not found -- build it with `make -C gstools-core_b200/csrc` "
+            "or `python -c 'import __graft_entry__ as g; g.build()'`. There is no CPU fallback." % _LIB_PATH)
+    L = ctypes.CDLL(_LIB_PATH)
+    a2 = [_vp, _i64, _i64]
+    a1 = [_vp, _i64]
+    head = [_int, _i64, _i64]
+    L.gsf_summate.argtypes = head + a2 + a1 + a1 + a2 + [_vp, _int]
+    L.gsf_summate_incompr.argtypes = head + a2 + a1 + a1 + a2 + [_vp, _i64, _i64, _int]
+    L.gsf_summate_fourier.argtypes = head + a1 + a2 + a1 + a1 + a2 + [_vp, _int]
+    L.gsf_summate_on_stream.argtypes = [_int] + head + a1 + a2 + a1 + a1 + a2 + [_vp, _i64, _i64, _vp]
+    L.gsf_set_devices.argtypes = [ctypes.POINTER(_int), _int]
+    L.gsf_set_chunk_points.argtypes = [_i64]
+    L.gsf_set_variant.argtypes = [_int, _int]
+    L.gsf_set_profiling.argtypes = [_int]
+    L.gsf_get_last_stats.argtypes = [ctypes.POINTER(GsfStats)]
+    L.gsf_dfma_peak.argtypes = [_int, ctypes.c_double, ctypes.POINTER(ctypes.c_double),
+                                ctypes.POINTER(ctypes.c_double)]
+    L.gsf_last_error.restype = ctypes.c_char_p
+    for name in ("gsf_summate", "gsf_summate_incompr", "gsf_summate_fourier", "gsf_summate_on_stream",
+                 "gsf_set_devices", "gsf_set_chunk_points", "gsf_set_variant", "gsf_set_profiling",
+                 "gsf_get_last_stats", "gsf_dfma_peak", "gsf_abi_version", "gsf_device_count",
+                 "gsf_shutdown"):
+        getattr(L, name).restype = _int
+    _lib = L
+    return L
+
+
+_ERR = {1: ValueError, 2: ValueError, 3: ValueError, 4: RuntimeError, 5: RuntimeError, 6: ValueError,
+        7: MemoryError}
+
+
+def _raise(rc):
+    msg = _load().gsf_last_error().decode("utf-8", "replace")
+    raise _ERR.get(rc, RuntimeError)("gstools_core (B200): %s [status %d]" % (msg, rc))
+
+
+# ---------------------------------------------------------------------------------------------
+# argument marshalling
+
+class _Arr:
+    """pointer + shape + element strides of a float64 host (numpy) or device (CUDA array interface) array"""
+    __slots__ = ("ptr", "shape", "strides", "keep", "device")
+
+    def __init__(self, obj, ndim, name):
+        cai = getattr(obj, "__cuda_array_interface__", None)
+        if cai is not None and not isinstance(obj, np.ndarray):
+            if cai["typestr"] not in ("<f8", "=f8", "f8"):
+                raise TypeError("argument '%s': device array must be float64, got %s" % (name, cai["typestr"]))
+            shape = tuple(cai["shape"])
+            st = cai.get("strides")
+            if st is None:
+                st, acc = [], 8
+                for s in reversed(shape):
+                    st.append(acc)
+                    acc *= s
+                st = tuple(reversed(st))
+            self.ptr = cai["data"][0]
+            self.device = True
+            self.keep = obj
+        else:
+            if not isinstance(obj, np.ndarray):
+                raise TypeError("argument '%s': 'ndarray' expected, got %s" % (name, type(obj).__name__))
+            if obj.dtype != np.float64:
+                # PyReadonlyArray<f64> does not cast (src/lib.rs:38-41): wrong dtype is a TypeError
+                raise TypeError("argument '%s': type mismatch: expected float64, got %s" % (name, obj.dtype))
+            shape, st = obj.shape, obj.strides
+            self.ptr = obj.ctypes.data
+            self.device = False
+            self.keep = obj
+        if len(shape) != ndim:
+            raise TypeError("argument '%s': dimensionality mismatch: expected %d, got %d" % (name, ndim, len(shape)))
+        if any(s % 8 for s in st):
+            raise ValueError("argument '%s': strides must be multiples of 8 bytes" % name)
+        self.shape = shape
+        self.strides = tuple(s // 8 for s in st)
+
+    def args(self):
+        return (self.ptr,) + self.strides
+
+
+def _threads(num_threads):
+    if num_threads is None:
+        return 0
+    n = int(num_threads)
+    if n < 0:
+        raise OverflowError("can't convert negative int to unsigned")   # Option<usize>, src/lib.rs:41
+    return n
+
+
+def _check_shapes(cov, z1, z2, pos):
+    # the reference's assert_eq!s, src/field.rs:44-46 / 104-106 / 227-229
+    if cov.shape[0] != pos.shape[0]:
+        raise ValueError("dim mismatch: cov_samples has %d rows, pos has %d" % (cov.shape[0], pos.shape[0]))
+    if cov.shape[1] != z1.shape[0] or cov.shape[1] != z2.shape[0]:
+        raise ValueError("mode count mismatch: cov_samples has %d modes, z1 %d, z2 %d"
+                         % (cov.shape[1], z1.shape[0], z2.shape[0]))
+
+
+def summate(cov_samples, z1, z2, pos, num_threads=None):
+    """Scalar randomization method (reference: summate_py, src/lib.rs:33-48 -> field::summator)."""
+    L = _load()
+    cov, a1, a2, p = _Arr(cov_samples, 2, "cov_samples"), _Arr(z1, 1, "z1"), _Arr(z2, 1, "z2"), _Arr(pos, 2, "pos")
+    _check_shapes(cov, a1, a2, p)
+    if p.device:
+        raise TypeError("summate: pos is a device array; use summate_device(..., out=...)")
+    d, n = cov.shape
+    m = p.shape[1]
+    out = np.empty(m, dtype=np.float64)
+    rc = L.gsf_summate(d, n, m, *cov.args(), *a1.args(), *a2.args(), *p.args(), out.ctypes.data,
+                       _threads(num_threads))
+    if rc:
+        _raise(rc)
+    return out
+
+
+def summate_incompr(cov_samples, z1, z2, pos, num_threads=None):
+    """Incompressible vector field (reference: summate_incompr_py, src/lib.rs:50-65).
+
+    Returns shape (d, M) in Fortran order, like the reference (src/field.rs:166-174)."""
+    L = _load()
+    cov, a1, a2, p = _Arr(cov_samples, 2, "cov_samples"), _Arr(z1, 1, "z1"), _Arr(z2, 1, "z2"), _Arr(pos, 2, "pos")
+    _check_shapes(cov, a1, a2, p)
+    if p.device:
+        raise TypeError("summate_incompr: pos is a device array; use summate_incompr_device(..., out=...)")
+    d, n = cov.shape
+    m = p.shape[1]
+    out = np.empty((d, m), dtype=np.float64, order="F")
+    rc = L.gsf_summate_incompr(d, n, m, *cov.args(), *a1.args(), *a2.args(), *p.args(), out.ctypes.data,
+                               out.strides[0] // 8, out.strides[1] // 8, _threads(num_threads))
+    if rc:
+        _raise(rc)
+    return out
+
+
+def summate_fourier(spectrum_factor, modes, z1, z2, pos, num_threads=None):
+    """Periodic Fourier method (reference: summate_fourier_py, src/lib.rs:67-84)."""
+    L = _load()
+    sf = _Arr(spectrum_factor, 1, "spectrum_factor")
+    cov, a1, a2, p = _Arr(modes, 2, "modes"), _Arr(z1, 1, "z1"), _Arr(z2, 1, "z2"), _Arr(pos, 2, "pos")
+    _check_shapes(cov, a1, a2, p)
+    if sf.shape[0] != cov.shape[1]:
+        # the reference panics inside ndarray's Zip::and (part dimension mismatch)
+        raise ValueError("spectrum_factor has %d entries, modes has %d" % (sf.shape[0], cov.shape[1]))
+    if p.device:
+        raise TypeError("summate_fourier: pos is a device array; use summate_fourier_device(..., out=...)")
+    d, n = cov.shape
+    m = p.shape[1]
+    out = np.empty(m, dtype=np.float64)
+    rc = L.gsf_summate_fourier(d, n, m, *sf.args(), *cov.args(), *a1.args(), *a2.args(), *p.args(),
+                               out.ctypes.data, _threads(num_threads))
+    if rc:
+        _raise(rc)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# device-resident, stream-ordered entry points
+
+def _on_stream(kind, sf, cov_samples, z1, z2, pos, out, stream):
+    L = _load()
+    cov, a1, a2, p = _Arr(cov_samples, 2, "cov_samples"), _Arr(z1, 1, "z1"), _Arr(z2, 1, "z2"), _Arr(pos, 2, "pos")
+    _check_shapes(cov, a1, a2, p)
+    d, n = cov.shape
+    m = p.shape[1]
+    o = _Arr(out, 2 if kind == 1 else 1, "out")
+    if not (p.device and o.device):
+        raise TypeError("*_device functions need pos and out in device memory")
+    if kind == 1:
+        if o.shape != (d, m):
+            raise ValueError("out must have shape (%d, %d)" % (d, m))
+        ostr = o.strides
+    else:
+        if o.shape != (m,) or (m > 1 and o.strides[0] != 1):
+            raise ValueError("out must be a contiguous array of %d float64" % m)
+        ostr = (0, 1)
+    if kind == 2:
+        s = _Arr(sf, 1, "spectrum_factor")
+        if s.shape[0] != n:
+            raise ValueError("spectrum_factor has %d entries, modes has %d" % (s.shape[0], n))
+        sargs = s.args()
+    else:
+        sargs = (None, 0)
+    rc = L.gsf_summate_on_stream(kind, d, n, m, *sargs, *cov.args(), *a1.args(), *a2.args(), *p.args(),
+                                 o.ptr, ostr[0], ostr[1], _vp(int(stream) if stream else 0))
+    if rc:
+        _raise(rc)
+    return out
+
+
+def summate_device(cov_samples, z1, z2, pos, out, stream=0):
+    """summate on device-resident pos/out, enqueued on `stream` (a cudaStream_t handle); no sync."""
+    return _on_stream(0, None, cov_samples, z1, z2, pos, out, stream)
+
+
+def summate_incompr_device(cov_samples, z1, z2, pos, out, stream=0):
+    return _on_stream(1, None, cov_samples, z1, z2, pos, out, stream)
+
+
+def summate_fourier_device(spectrum_factor, modes, z1, z2, pos, out, stream=0):
+    return _on_stream(2, spectrum_factor, modes, z1, z2, pos, out, stream)
+
+
+# ---------------------------------------------------------------------------------------------
+# context / diagnostics
+
+def device_count():
+    return _load().gsf_device_count()
+
+
+def set_devices(device_ids=None):
+    """Devices that host-memory calls shard their points over (None = default: GSF_DEVICES or [0])."""
+    L = _load()
+    ids = list(device_ids or [])
+    arr = (_int * max(len(ids), 1))(*ids)
+    rc = L.gsf_set_devices(arr, len(ids))
+    if rc:
+        _raise(rc)
+
+
+def set_chunk_points(n):
+    rc = _load().gsf_set_chunk_points(int(n))
+    if rc:
+        _raise(rc)
+
+
+def set_variant(points_per_thread=0, lanes_per_point=0):
+    rc = _load().gsf_set_variant(int(points_per_thread), int(lanes_per_point))
+    if rc:
+        _raise(rc)
+
+
+def set_profiling(enabled=True):
+    _load().gsf_set_profiling(1 if enabled else 0)
+
+
+def last_stats():
+    s = GsfStats()
+    rc = _load().gsf_get_last_stats(ctypes.byref(s))
+    if rc:
+        _raise(rc)
+    return s.as_dict()
+
+
+def dfma_peak(device=0, min_ms=200.0):
+    """Measured FP64 DFMA rate of `device` in thread-level DFMA/s (the roofline denominator)."""
+    rate, ms = ctypes.c_double(), ctypes.c_double()
+    rc = _load().gsf_dfma_peak(int(device), float(min_ms), ctypes.byref(rate), ctypes.byref(ms))
+    if rc:
+        _raise(rc)
+    return rate.value, ms.value
+
+
+def shutdown():
+    _load().gsf_shutdown()

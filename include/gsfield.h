@@ -1,0 +1,144 @@
+/*
+ * gsfield.h -- C ABI of the B200-native randomization-method field summation.
+ *
+ * Drop-in boundary for GSTools-Core's `field::summator*` hot path.  Each entry point is what the
+ * reference's own Rust function body (and through it the pyo3 module) binds after dispatching to
+ * the CUDA path; see INTEGRATION.md for the Rust `extern "C"` block and the ctypes binding.
+ *
+ *   gsf_summate          replaces field::summator          /root/reference/src/field.rs:37-65
+ *   gsf_summate_incompr  replaces field::summator_incompr  /root/reference/src/field.rs:97-182
+ *   gsf_summate_fourier  replaces field::summator_fourier  /root/reference/src/field.rs:219-249
+ *
+ * Conventions
+ *   - Every array is f64 and addressed as base[i*stride0 + j*stride1] with ELEMENT strides, so any
+ *     ndarray / numpy view the reference accepts (src/lib.rs:43-46) can be passed without a copy.
+ *   - The caller owns every buffer and pre-allocates the output.  The library owns device buffers,
+ *     streams and pinned staging inside a lazily created process-wide context (gsf_shutdown frees it).
+ *   - `pos` and `out` may live in pageable host memory, pinned host memory or device memory; the
+ *     library detects which (cudaPointerGetAttributes).  Host data is streamed through the GPU in
+ *     chunks (H2D / kernel / D2H overlapped); device-resident data is processed in place.
+ *   - `num_threads` is accepted for signature compatibility with the reference (src/field.rs:42);
+ *     it never affects results.  <= 0 means "default".
+ *   - Return value: GSF_OK or an error code; gsf_last_error() gives a thread-local message.  The
+ *     library never aborts and never throws across the ABI (the reference panics => abort,
+ *     Cargo.toml:22; a Rust shim turns a non-zero status back into panic!).
+ *   - There is NO CPU fallback: without a usable CUDA device every compute entry point returns
+ *     GSF_ERR_NO_DEVICE.
+ *   - Calls are serialised per process by an internal mutex; callable from any thread.
+ */
+#ifndef GSFIELD_H
+#define GSFIELD_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSF_ABI_VERSION 1
+
+enum gsf_status {
+    GSF_OK = 0,
+    GSF_ERR_DIM = 1,        /* dim < 1, dim > GSF_MAX_DIM, or incompr with dim not in {2,3} (field.rs:180) */
+    GSF_ERR_SHAPE = 2,      /* negative sizes / inconsistent arguments (field.rs:44-46 asserts)          */
+    GSF_ERR_EMPTY_MODES = 3,/* summator_incompr with 0 modes (reduce_with(..).unwrap(), field.rs:163)    */
+    GSF_ERR_NO_DEVICE = 4,  /* no CUDA device / driver; there is no CPU path                             */
+    GSF_ERR_CUDA = 5,       /* a CUDA runtime call failed (message has the details)                      */
+    GSF_ERR_ARG = 6,        /* NULL pointer, bad device id, mixed device/host placement not supported    */
+    GSF_ERR_ALLOC = 7       /* host or device allocation failed                                          */
+};
+
+#define GSF_MAX_DIM 8
+
+/* Per-call statistics of the most recent compute call on this thread's context. Times in ms. */
+typedef struct gsf_stats {
+    double total_ms;        /* host wall clock of the whole call                                        */
+    double kernel_ms;       /* summation kernel(s): CUDA events on the launching stream(s), summed over
+                               chunks, max over devices                                                  */
+    double prep_ms;         /* mode pre-processing kernel                                                */
+    int64_t point_modes;    /* n_points * n_modes                                                        */
+    int64_t h2d_bytes;      /* bytes copied host->device                                                 */
+    int64_t d2h_bytes;      /* bytes copied device->host                                                 */
+    int32_t kernel_launches;/* number of kernels launched by this call (prep + summation)                */
+    int32_t n_devices;      /* devices that took part                                                    */
+    int32_t n_chunks;       /* pipeline chunks (over all devices)                                        */
+    int32_t points_per_thread; /* P of the kernel variant used                                          */
+    int32_t lanes_per_point;   /* L of the kernel variant used                                          */
+    int32_t pos_memory;     /* 0 pageable host, 1 pinned host, 2 device                                  */
+    int32_t out_memory;
+    int32_t reserved;
+} gsf_stats;
+
+/* ---- the three reference functions ------------------------------------------------------- */
+
+/* out[j] = sum_i z1[i]*cos(<k_i,x_j>) + z2[i]*sin(<k_i,x_j>);  out: n_points contiguous f64. */
+int gsf_summate(int dim, int64_t n_modes, int64_t n_points,
+                const double *cov_samples, int64_t cov_s0, int64_t cov_s1, /* (dim, n_modes)  */
+                const double *z1, int64_t z1_s,                            /* (n_modes)       */
+                const double *z2, int64_t z2_s,                            /* (n_modes)       */
+                const double *pos, int64_t pos_s0, int64_t pos_s1,         /* (dim, n_points) */
+                double *out, int num_threads);
+
+/* out[a*out_s0 + j*out_s1] = sum_i p_a(k_i) * (z1 cos + z2 sin);  dim in {2,3}.  The reference
+ * returns shape (dim, n_points) in Fortran order (field.rs:166-174): out_s0 = 1, out_s1 = dim. */
+int gsf_summate_incompr(int dim, int64_t n_modes, int64_t n_points,
+                        const double *cov_samples, int64_t cov_s0, int64_t cov_s1,
+                        const double *z1, int64_t z1_s,
+                        const double *z2, int64_t z2_s,
+                        const double *pos, int64_t pos_s0, int64_t pos_s1,
+                        double *out, int64_t out_s0, int64_t out_s1, int num_threads);
+
+/* out[j] = sum_i sf[i] * (z1[i]*cos(<k_i,x_j>) + z2[i]*sin(<k_i,x_j>)). */
+int gsf_summate_fourier(int dim, int64_t n_modes, int64_t n_points,
+                        const double *spectrum_factor, int64_t sf_s,       /* (n_modes)       */
+                        const double *modes, int64_t modes_s0, int64_t modes_s1,
+                        const double *z1, int64_t z1_s,
+                        const double *z2, int64_t z2_s,
+                        const double *pos, int64_t pos_s0, int64_t pos_s1,
+                        double *out, int num_threads);
+
+/* ---- stream-ordered variant for device-resident data -------------------------------------- */
+
+/* kind: 0 summate, 1 summate_incompr, 2 summate_fourier.  pos and out must be device pointers on
+ * the same device; mode arrays may be host or device.  Work is enqueued on `cuda_stream`
+ * (a cudaStream_t; NULL = legacy default stream) and the call returns without synchronising.
+ * spectrum_factor is ignored unless kind == 2; out strides are ignored unless kind == 1
+ * (scalar outputs are contiguous). */
+int gsf_summate_on_stream(int kind, int dim, int64_t n_modes, int64_t n_points,
+                          const double *spectrum_factor, int64_t sf_s,
+                          const double *cov_samples, int64_t cov_s0, int64_t cov_s1,
+                          const double *z1, int64_t z1_s,
+                          const double *z2, int64_t z2_s,
+                          const double *pos, int64_t pos_s0, int64_t pos_s1,
+                          double *out, int64_t out_s0, int64_t out_s1,
+                          void *cuda_stream);
+
+/* ---- context / diagnostics ---------------------------------------------------------------- */
+
+int gsf_abi_version(void);
+/* Number of CUDA devices visible (0 if none / no driver). */
+int gsf_device_count(void);
+/* Devices the host-memory entry points shard points over (contiguous ranges, no collective).
+ * n == 0 restores the default: env GSF_DEVICES="0,1,.." if set, else device 0 only. */
+int gsf_set_devices(const int *device_ids, int n);
+/* Points per pipeline chunk for host-resident data (0 = default). */
+int gsf_set_chunk_points(int64_t chunk_points);
+/* Force the kernel variant (0,0 = heuristic).  P in {1,2,4}, L in {1,2,4,8,16,32}. */
+int gsf_set_variant(int points_per_thread, int lanes_per_point);
+/* Enable CUDA-event timing of the kernels (fills kernel_ms / prep_ms; adds event-sync overhead
+ * only in gsf_get_last_stats). */
+int gsf_set_profiling(int enabled);
+int gsf_get_last_stats(gsf_stats *out);
+const char *gsf_last_error(void);
+/* Frees all device / pinned memory and streams.  The context is re-created on the next call. */
+int gsf_shutdown(void);
+
+/* Micro-benchmark: sustained FP64 DFMA issue rate of `device` in DFMA (thread-level) per second,
+ * measured with CUDA events over ~`min_ms` milliseconds of dependent-chain DFMAs at full
+ * occupancy.  This is the measured roofline denominator. */
+int gsf_dfma_peak(int device, double min_ms, double *dfma_per_s, double *elapsed_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSFIELD_H */

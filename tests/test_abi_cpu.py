@@ -1,0 +1,102 @@
+"""CPU-side checks of the C-ABI library and the Python mirror module (no GPU needed).
+
+Covers: libgsfield.so loads and exports every symbol include/gsfield.h declares; argument
+validation mirrors the reference's asserts/panics (src/field.rs:44-46,104-106,177-181,163);
+and the product path fails loudly -- no CPU fallback -- when no CUDA device is present.
+"""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import gstools_core as gc
+from conftest import ROOT
+
+HAVE_GPU = gc.device_count() > 0
+
+
+def test_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "gsfield.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(gsf_[a-z_0-9]+)\s*\(", hdr))
+    assert {"gsf_summate", "gsf_summate_incompr", "gsf_summate_fourier", "gsf_summate_on_stream",
+            "gsf_dfma_peak", "gsf_get_last_stats"} <= names
+    lib = ctypes.CDLL(os.path.join(ROOT, "gstools-core_b200", "gstools_core", "libgsfield.so"))
+    for n in sorted(names):
+        assert hasattr(lib, n), "libgsfield.so does not export %s" % n
+    assert lib.gsf_abi_version() == 1
+
+
+def test_module_surface_matches_reference():
+    # src/lib.rs:29-84: __version__, summate, summate_incompr, summate_fourier
+    for n in ("__version__", "summate", "summate_incompr", "summate_fourier"):
+        assert hasattr(gc, n)
+    import inspect
+    assert list(inspect.signature(gc.summate).parameters) == ["cov_samples", "z1", "z2", "pos", "num_threads"]
+    assert list(inspect.signature(gc.summate_incompr).parameters) == ["cov_samples", "z1", "z2", "pos", "num_threads"]
+    assert list(inspect.signature(gc.summate_fourier).parameters) == [
+        "spectrum_factor", "modes", "z1", "z2", "pos", "num_threads"]
+
+
+def test_dtype_and_rank_are_type_errors():
+    k = np.ones((2, 3)); z = np.ones(3); pos = np.ones((2, 4))
+    with pytest.raises(TypeError):
+        gc.summate(k.astype(np.float32), z, z, pos)       # PyReadonlyArray<f64> never casts
+    with pytest.raises(TypeError):
+        gc.summate(k, z, z, [[1.0, 2.0], [3.0, 4.0]])     # not an ndarray
+    with pytest.raises(TypeError):
+        gc.summate(k, z.reshape(3, 1), z, pos)            # rank mismatch
+    with pytest.raises(OverflowError):
+        gc.summate(k, z, z, pos, num_threads=-1)          # Option<usize>
+
+
+def test_shape_mismatch_is_value_error():
+    k = np.ones((2, 3)); z = np.ones(3)
+    with pytest.raises(ValueError):
+        gc.summate(k, z, z, np.ones((3, 4)))              # field.rs:44
+    with pytest.raises(ValueError):
+        gc.summate(k, np.ones(4), z, np.ones((2, 4)))     # field.rs:45
+    with pytest.raises(ValueError):
+        gc.summate_incompr(k, z, np.ones(2), np.ones((2, 4)))  # field.rs:106
+    with pytest.raises(ValueError):
+        gc.summate_fourier(np.ones(2), k, z, z, np.ones((2, 4)))
+
+
+def test_c_abi_validation_codes():
+    L = gc._load()
+    z = np.ones(3); k = np.ones((9, 3)); pos = np.ones((9, 4)); out = np.zeros(4)
+    rc = L.gsf_summate(9, 3, 4, k.ctypes.data, 3, 1, z.ctypes.data, 1, z.ctypes.data, 1,
+                       pos.ctypes.data, 4, 1, out.ctypes.data, 0)
+    assert rc == 1 and b"dim" in L.gsf_last_error()                       # GSF_ERR_DIM
+    rc = L.gsf_summate_incompr(1, 3, 4, k.ctypes.data, 3, 1, z.ctypes.data, 1, z.ctypes.data, 1,
+                               pos.ctypes.data, 4, 1, out.ctypes.data, 1, 1, 0)
+    assert rc == 1 and b"two- and three-dimensional" in L.gsf_last_error()  # field.rs:180
+    rc = L.gsf_summate_incompr(2, 0, 4, k.ctypes.data, 3, 1, z.ctypes.data, 1, z.ctypes.data, 1,
+                               pos.ctypes.data, 4, 1, out.ctypes.data, 1, 2, 0)
+    assert rc == 3                                                         # GSF_ERR_EMPTY_MODES, field.rs:163
+    rc = L.gsf_summate(2, -1, 4, k.ctypes.data, 3, 1, z.ctypes.data, 1, z.ctypes.data, 1,
+                       pos.ctypes.data, 4, 1, out.ctypes.data, 0)
+    assert rc == 2                                                         # GSF_ERR_SHAPE
+    rc = L.gsf_summate(2, 3, 4, None, 3, 1, z.ctypes.data, 1, z.ctypes.data, 1,
+                       pos.ctypes.data, 4, 1, out.ctypes.data, 0)
+    assert rc == 6                                                         # GSF_ERR_ARG
+
+
+def test_incompr_python_errors():
+    with pytest.raises(ValueError):
+        gc.summate_incompr(np.ones((1, 3)), np.ones(3), np.ones(3), np.ones((1, 4)))
+    with pytest.raises(ValueError):
+        gc.summate_incompr(np.ones((2, 0)), np.ones(0), np.ones(0), np.ones((2, 4)))
+
+
+@pytest.mark.skipif(HAVE_GPU, reason="checks the no-device behaviour")
+def test_no_device_fails_loudly():
+    k = np.ones((2, 3)); z = np.ones(3); pos = np.ones((2, 4))
+    for call in (lambda: gc.summate(k, z, z, pos),
+                 lambda: gc.summate_incompr(k, z, z, pos),
+                 lambda: gc.summate_fourier(z, k, z, z, pos),
+                 lambda: gc.dfma_peak(0, 1.0)):
+        with pytest.raises(RuntimeError, match="no CUDA device"):
+            call()

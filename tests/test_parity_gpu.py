@@ -1,0 +1,244 @@
+"""GPU parity tests: the CUDA path (through the C ABI / the gstools_core mirror module) against
+the CPU oracle on identical inputs.
+
+Acceptance (BASELINE.json north_star):
+    max |gpu - oracle| <= 1e-9 * sigma,  sigma = population std of the oracle output
+and the reference's own known-answer vectors (src/field.rs:346-355,371-380,396-427) to 1e-13 abs.
+Bitwise equality is NOT expected: the kernels use FMA and a single-cos formulation.
+"""
+import numpy as np
+import pytest
+
+import gstools_core as gc
+import oracle
+from gstools_core import workloads
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9          # x sigma, the north_star tolerance
+KAT_ABS = 1e-13
+
+
+def _need_gpu():
+    if gc.device_count() < 1:
+        pytest.fail("no CUDA device: the gpu-marked tests must run on the B200 box")
+
+
+@pytest.fixture(autouse=True)
+def _reset():
+    _need_gpu()
+    gc.set_variant(0, 0)
+    gc.set_chunk_points(0)
+    gc.set_devices(None)
+    yield
+
+
+def rel_err(got, ref):
+    sigma = float(np.std(ref))
+    if not np.isfinite(sigma) or sigma == 0.0:
+        sigma = 1.0
+    return float(np.max(np.abs(got - ref))) / sigma
+
+
+# ------------------------------------------------------------------------------- goldens
+def test_kat_summate(kat):
+    out = gc.summate(kat["cov_samples"], kat["z_1"], kat["z_2"], kat["pos"])
+    assert out.shape == (8,) and out.dtype == np.float64
+    assert np.max(np.abs(out - kat["summate"])) <= KAT_ABS
+
+
+def test_kat_fourier(kat):
+    out = gc.summate_fourier(kat["spectrum_factor"], kat["cov_samples"], kat["z_1"], kat["z_2"], kat["pos"])
+    assert np.max(np.abs(out - kat["summate_fourier"])) <= KAT_ABS
+
+
+def test_kat_incompr(kat):
+    out = gc.summate_incompr(kat["cov_samples"], kat["z_1"], kat["z_2"], kat["pos"])
+    assert out.shape == (3, 8) and out.flags.f_contiguous     # src/field.rs:166-174
+    assert np.max(np.abs(out - kat["summate_incompr"])) <= KAT_ABS
+
+
+# ------------------------------------------------------------------------------- random parity
+def _rand(seed, d, n, m, heavy=False, span=50.0):
+    rng = np.random.default_rng(seed)
+    k = rng.normal(size=(d, n))
+    if heavy:
+        k = k / np.abs(rng.normal(size=n))                    # multivariate-t tails (C2/C5-like)
+    z1, z2 = rng.normal(size=n), rng.normal(size=n)
+    pos = rng.uniform(-span, span, size=(d, m))
+    return k, z1, z2, pos
+
+
+@pytest.mark.parametrize("d", [1, 2, 3, 4, 5, 8])
+@pytest.mark.parametrize("n,m", [(1, 1), (10, 8), (257, 1031), (1000, 4099)])
+def test_summate_random(d, n, m):
+    k, z1, z2, pos = _rand(100 + d, d, n, m, heavy=(d == 3))
+    ref = oracle.summate(k, z1, z2, pos)
+    got = gc.summate(k, z1, z2, pos)
+    assert got.shape == ref.shape
+    assert rel_err(got, ref) <= TOL
+
+
+@pytest.mark.parametrize("d", [2, 3])
+@pytest.mark.parametrize("n,m", [(1, 1), (10, 8), (257, 1031), (1000, 4099)])
+def test_incompr_random(d, n, m):
+    k, z1, z2, pos = _rand(200 + d, d, n, m)
+    ref = oracle.summate_incompr(k, z1, z2, pos)
+    got = gc.summate_incompr(k, z1, z2, pos)
+    assert got.shape == (d, m) and got.flags.f_contiguous
+    assert rel_err(got, ref) <= TOL
+
+
+@pytest.mark.parametrize("d", [1, 2, 3])
+def test_fourier_random(d):
+    k, z1, z2, pos = _rand(300 + d, d, 513, 2050)
+    sf = np.random.default_rng(9).normal(size=513)            # the reference's KAT uses signed factors
+    ref = oracle.summate_fourier(sf, k, z1, z2, pos)
+    got = gc.summate_fourier(sf, k, z1, z2, pos)
+    assert rel_err(got, ref) <= TOL
+
+
+# ------------------------------------------------------------------------------- kernel variants
+@pytest.mark.parametrize("P,L", [(4, 1), (2, 1), (1, 1), (2, 2), (2, 4), (2, 8), (2, 16), (2, 32),
+                                 (1, 2), (1, 4), (1, 8), (1, 16), (1, 32)])
+def test_all_variants_agree(P, L):
+    k, z1, z2, pos = _rand(7, 3, 700, 3001, heavy=True)
+    ref = oracle.summate(k, z1, z2, pos)
+    refi = oracle.summate_incompr(k, z1, z2, pos)
+    gc.set_variant(P, L)
+    got = gc.summate(k, z1, z2, pos)
+    assert gc.last_stats()["points_per_thread"] == P and gc.last_stats()["lanes_per_point"] == L
+    assert rel_err(got, ref) <= TOL
+    goti = gc.summate_incompr(k, z1, z2, pos)
+    assert rel_err(goti, refi) <= TOL
+    k2, z1, z2, pos2 = _rand(8, 2, 300, 1500)
+    gc.set_variant(P, L)
+    assert rel_err(gc.summate(k2, z1, z2, pos2), oracle.summate(k2, z1, z2, pos2)) <= TOL
+
+
+def test_deterministic_repeat():
+    k, z1, z2, pos = _rand(11, 3, 999, 70001, heavy=True)
+    a = gc.summate(k, z1, z2, pos)
+    b = gc.summate(k, z1, z2, pos)
+    assert np.array_equal(a, b)                               # fixed-order sums: bit-reproducible
+
+
+# ------------------------------------------------------------------------------- layouts / memory kinds
+def test_strided_views():
+    k, z1, z2, pos = _rand(21, 3, 64, 5000)
+    ref = oracle.summate(k, z1, z2, pos)
+    kf = np.asfortranarray(k)
+    posf = np.asfortranarray(pos)                             # AoS positions
+    zz = np.zeros(2 * 64); zz[::2] = z1
+    big = np.zeros((3, 10000)); big[:, ::2] = pos
+    assert rel_err(gc.summate(kf, zz[::2], z2, posf), ref) <= TOL
+    assert rel_err(gc.summate(k, z1, z2, big[:, ::2]), ref) <= TOL
+    assert rel_err(gc.summate(k[:, ::-1], z1[::-1], z2[::-1], pos), ref) <= 1e-12 * 64  # other mode order
+
+
+def test_chunk_boundaries_and_pipeline():
+    k, z1, z2, pos = _rand(31, 3, 50, 300_000)
+    ref = oracle.summate(k, z1, z2, pos, oracle.max_threads())
+    refi = oracle.summate_incompr(k, z1, z2, pos)
+    for chunk in (1024, 33 * 1024, 1 << 20):
+        gc.set_chunk_points(chunk)
+        got = gc.summate(k, z1, z2, pos)
+        st = gc.last_stats()
+        assert st["n_chunks"] == -(-300_000 // min(chunk, 300_000))   # chunk is already a multiple of 1024
+        assert rel_err(got, ref) <= TOL
+        assert rel_err(gc.summate_incompr(k, z1, z2, pos), refi) <= TOL
+
+
+def test_pinned_and_device_memory():
+    torch = pytest.importorskip("torch")
+    k, z1, z2, pos = _rand(41, 3, 128, 200_000)
+    ref = oracle.summate(k, z1, z2, pos, oracle.max_threads())
+    refi = oracle.summate_incompr(k, z1, z2, pos)
+    # pinned host input
+    tp = torch.from_numpy(pos).pin_memory()
+    got = gc.summate(k, z1, z2, tp.numpy())
+    assert gc.last_stats()["pos_memory"] == 1
+    assert rel_err(got, ref) <= TOL
+    # device-resident, stream ordered
+    dpos = torch.from_numpy(pos).cuda()
+    dout = torch.empty(pos.shape[1], dtype=torch.float64, device="cuda")
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        gc.summate_device(k, z1, z2, dpos, dout, stream=s.cuda_stream)
+    s.synchronize()
+    assert rel_err(dout.cpu().numpy(), ref) <= TOL
+    # device modes too, incompr with both output layouts
+    dk, dz1, dz2 = (torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in (k, z1, z2))
+    douti = torch.empty((3, pos.shape[1]), dtype=torch.float64, device="cuda")
+    gc.summate_incompr_device(dk, dz1, dz2, dpos, douti, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert rel_err(douti.cpu().numpy(), refi) <= TOL
+    doutf = torch.empty((pos.shape[1], 3), dtype=torch.float64, device="cuda").t()   # F-ordered (3, M)
+    gc.summate_incompr_device(dk, dz1, dz2, dpos, doutf, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert rel_err(doutf.cpu().numpy(), refi) <= TOL
+
+
+# ------------------------------------------------------------------------------- edge cases
+def test_edge_cases():
+    pos = np.ones((2, 5))
+    z0 = np.zeros(0)
+    assert np.array_equal(gc.summate(np.zeros((2, 0)), z0, z0, pos), np.zeros(5))       # fold identity
+    assert np.array_equal(gc.summate_fourier(z0, np.zeros((2, 0)), z0, z0, pos), np.zeros(5))
+    assert gc.summate(np.ones((2, 3)), np.ones(3), np.ones(3), np.ones((2, 0))).shape == (0,)
+    assert gc.summate_incompr(np.ones((2, 3)), np.ones(3), np.ones(3), np.ones((2, 0))).shape == (2, 0)
+    out = gc.summate_incompr(np.zeros((2, 1)), np.ones(1), np.ones(1), pos)
+    assert np.isnan(out).all()                                                          # k = 0 -> 0/0
+    # non-finite inputs propagate like sin/cos(inf) = NaN
+    k = np.array([[1.0, np.inf], [0.5, 1.0]])
+    got = gc.summate(k, np.ones(2), np.ones(2), pos)
+    assert np.isnan(got).all()
+    got = gc.summate(np.ones((2, 2)), np.array([1.0, np.nan]), np.ones(2), pos)
+    assert np.isnan(got).all()
+    # zero amplitude mode contributes nothing
+    k = np.array([[1.0, 2.0], [0.5, 1.0]])
+    a = gc.summate(k, np.array([1.0, 0.0]), np.array([2.0, 0.0]), pos)
+    b = gc.summate(k[:, :1], np.array([1.0]), np.array([2.0]), pos)
+    assert np.allclose(a, b, rtol=0, atol=1e-15)
+
+
+def test_large_phases():
+    # |phase| up to ~1e6 rad as in C5 (SURVEY.md section 7 "heavy-tailed spectra")
+    rng = np.random.default_rng(5)
+    k = rng.normal(size=(3, 400)) * 1e4
+    z1, z2 = rng.normal(size=400), rng.normal(size=400)
+    pos = rng.uniform(0, 100, size=(3, 2000))
+    ref = oracle.summate(k, z1, z2, pos)
+    assert rel_err(gc.summate(k, z1, z2, pos), ref) <= TOL
+
+
+# ------------------------------------------------------------------------------- BASELINE configs
+@pytest.mark.parametrize("cfg,scale", [("c1", 1.0), ("c2", 0.02), ("c3", 0.02), ("c4", 0.0005), ("c5", 0.00005)])
+def test_baseline_configs_scaled(cfg, scale):
+    w = workloads.make(cfg, scale)
+    ref = getattr(oracle, w["kind"])(*w["args"], oracle.max_threads())
+    got = getattr(gc, w["kind"])(*w["args"])
+    e = rel_err(got, ref)
+    print(cfg, "m=%d n=%d max|d|/sigma=%.3g" % (w["m"], w["n"], e))
+    assert e <= TOL
+
+
+def test_c2_full_size_subset_and_linearity():
+    """C2 at full size: oracle on a strided point subset + linearity in (z1, z2)."""
+    w = workloads.make("c2")
+    k, z1, z2, pos = w["args"]
+    got = gc.summate(k, z1, z2, pos)
+    idx = np.unique(np.concatenate([np.arange(0, w["m"], 499), np.arange(1024), np.arange(w["m"] - 1024, w["m"])]))
+    ref = oracle.summate(k, z1, z2, np.ascontiguousarray(pos[:, idx]), oracle.max_threads())
+    assert rel_err(got[idx], ref) <= TOL
+    # linearity: f(2*z1 + a, 2*z2 + b) = 2 f(z1, z2) + f(a, b)
+    rng = np.random.default_rng(0)
+    a, b = rng.normal(size=z1.size), rng.normal(size=z1.size)
+    lhs = gc.summate(k, 2 * z1 + a, 2 * z2 + b, pos)
+    rhs = 2 * got + gc.summate(k, a, b, pos)
+    assert np.max(np.abs(lhs - rhs)) <= TOL * np.std(got)
+
+
+def test_dfma_peak_runs():
+    rate, ms = gc.dfma_peak(0, 20.0)
+    assert rate > 1e12 and ms > 0
