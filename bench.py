@@ -1,0 +1,359 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the B200 field summation (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|...]
+
+A "step" is one pass of the hot path (field::summator) over one batch of synthetic input.  The
+default workload is BASELINE.json configs[1] (C2): 3-D Exponential covariance, 1000 modes x 10^6
+points (100^3 grid), per GPU.  Under torchrun (N > 1) every rank runs the same-sized shard on its
+own GPU with no data-path collective (the path is embarrassingly parallel over points): weak
+scaling, value = points*modes of all ranks / max-over-ranks time.
+
+Two numbers per run:
+  value : kernel path, inputs already resident in HBM, CUDA events on the launching stream.
+  e2e   : the reference-facing call gstools_core.summate(...) with HOST buffers (pinned input,
+          host result), H2D and D2H inside the timed region.
+
+`--impl reference` times the reference algorithm's CPU restatement (oracle/, OpenMP over all host
+cores; the Rust crate itself cannot be built in this image -- no cargo/rustc) on a bounded sample
+of the same workload, scaled linearly in the number of points.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "gstools-core_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "field::summator Gpoint*modes/s (f64)"
+UNIT = "Gpoint*modes/s"
+L2_BYTES = 126 * 1024 * 1024
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the number of points (debug)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peak_file():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(prefix="gsf_clocks_", suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "50"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw = [], [], []
+        reasons = set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            # "under load": samples whose power is above the midpoint between idle and max
+            thr = (min(pw) + max(pw)) / 2 if max(pw) - min(pw) > 50 else -1
+            load = [s for s, p in zip(sm, pw) if p >= thr] or sm
+            out.update(sm_mhz=statistics.median(load), sm_max_mhz=max(mx), reasons=sorted(reasons),
+                       samples=len(sm), power_w_max=max(pw))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_rate(w, seconds, threads=None):
+    """Oracle (C restatement of the Rayon path) on a bounded point sample; returns (Gpm/s, info)."""
+    import oracle
+    from gstools_core import workloads
+
+    threads = threads or oracle.max_threads()
+    fn = getattr(oracle, w["kind"])
+    n, m = w["n"], w["m"]
+    # probe to size the sample
+    m0 = min(m, max(threads * 64, 4096))
+    idx = np.linspace(0, m - 1, m0).astype(np.int64)
+    sub = workloads.subset_points(w, idx)
+    t0 = time.perf_counter(); fn(*sub["args"], threads); dt = time.perf_counter() - t0
+    rate = m0 * n / max(dt, 1e-9)
+    ms = int(min(m, max(m0, rate * seconds / n)))
+    idx = np.linspace(0, m - 1, ms).astype(np.int64)
+    sub = workloads.subset_points(w, idx)
+    t0 = time.perf_counter(); fn(*sub["args"], threads); dt = time.perf_counter() - t0
+    gpm = ms * n / dt / 1e9
+    info = {"value": gpm, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "%d of %d points x %d modes (evenly strided), %.2f s; cost is linear in points"
+                      % (ms, m, n, dt)}
+    return gpm, info, (sub, ms, dt)
+
+
+def run_reference(args):
+    """--impl reference: the CPU restatement with all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    from gstools_core import workloads
+
+    w = workloads.make(args.workload, args.scale)
+    threads = oracle.max_threads()
+    steps = max(1, min(args.steps, 5))
+    warm = max(1, min(args.warmup, 1))
+    per_step = max(1.0, min(20.0, 60.0 / (steps + warm)))
+    _, info, (sub, ms, _dt) = cpu_reference_rate(w, per_step, threads)
+    fn = getattr(oracle, w["kind"])
+    for _ in range(warm):
+        fn(*sub["args"], threads)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn(*sub["args"], threads)
+    dt = (time.perf_counter() - t0) / steps
+    gpm = ms * w["n"] / dt / 1e9
+    info.update(value=gpm, sample="%d of %d points x %d modes per step (evenly strided); linear in points"
+                % (ms, w["m"], w["n"]))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": gpm, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3 * (w["m"] / ms), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.workload), "note": "ms_per_step extrapolated to the full point count"},
+        "cpu_baseline": info,
+        "e2e": {"value": gpm, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_name(c):
+    return {
+        "c1": "C1 field::summator 2D Gaussian, 100 modes x 1e4 points",
+        "c2": "C2 field::summator 3D Exponential, 1000 modes x 1e6 points (100^3 grid) per GPU",
+        "c3": "C3 field::summator_incompr 3D, 1000 modes x 1e6 points per GPU",
+        "c4": "C4 field::summator_fourier 2D, 1e4 modes x 4096^2 points per GPU",
+        "c5": "C5 field::summator 3D, 1e4 modes x 1e8 points per GPU",
+    }[c]
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import gstools_core as gc
+    from gstools_core import workloads
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available() or gc.device_count() < 1:
+        raise RuntimeError("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    gc.set_devices([local])
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    w = workloads.make(args.workload, args.scale)
+    kind, n, m, d = w["kind"], w["n"], w["m"], w["d"]
+    pm = n * m
+    nc = d if kind == "summate_incompr" else 1
+    W, K = max(args.warmup, 3), max(args.steps, 1)
+
+    # ---- device-resident inputs: rotate over enough copies that a step's input was evicted from
+    # L2 by the time it is reused (sets * (pos + out) > L2)
+    pos_bytes, out_bytes = d * m * 8, nc * m * 8
+    n_sets = max(2, -(-2 * L2_BYTES // (pos_bytes + out_bytes)))
+    n_sets = min(n_sets, 16)
+    margs = w["args"][:-1]
+    pos_host = w["args"][-1]
+    dev_modes = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in margs]
+    dev_pos = [torch.from_numpy(pos_host).cuda() for _ in range(n_sets)]
+    oshape = (m, nc) if nc > 1 else (m,)
+    dev_out = [torch.empty(oshape, dtype=torch.float64, device="cuda") for _ in range(n_sets)]
+    dev_fn = getattr(gc, kind + "_device")
+    stream = torch.cuda.current_stream()
+
+    def dev_step(i):
+        o = dev_out[i % n_sets]
+        dev_fn(*dev_modes, dev_pos[i % n_sets], o.t() if nc > 1 else o, stream=stream.cuda_stream)
+
+    gc.set_profiling(False)
+    for i in range(W):
+        dev_step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for i in range(K):
+        dev_step(i)
+        launches += gc.last_stats()["kernel_launches"]
+    e1.record(stream)
+    barrier()
+    dev_ms = max_over_ranks(e0.elapsed_time(e1)) / K
+    variant = gc.last_stats()
+
+    # ---- dominant kernel alone: library-side CUDA events on the launching stream, per launch
+    gc.set_profiling(True)
+    kms = []
+    for i in range(min(K, 20)):
+        dev_step(i)
+        torch.cuda.synchronize()
+        kms.append(gc.last_stats()["kernel_ms"])
+    gc.set_profiling(False)
+    kernel_ms = statistics.mean(kms)
+
+    # ---- end to end through the reference-facing API: pinned host input, host result
+    host_fn = getattr(gc, kind)
+    pin = [torch.from_numpy(pos_host).pin_memory() for _ in range(2)]
+    pin_np = [p.numpy() for p in pin]
+    for i in range(W):
+        host_fn(*margs, pin_np[i % 2])
+    barrier()
+    e2e_launches = 0
+    t0 = time.perf_counter()
+    for i in range(K):
+        res = host_fn(*margs, pin_np[i % 2])
+        e2e_launches += gc.last_stats()["kernel_launches"]
+    torch.cuda.synchronize()
+    e2e_local = (time.perf_counter() - t0) * 1e3
+    st = gc.last_stats()
+    barrier()
+    e2e_ms = max_over_ranks(e2e_local) / K
+    checksum = float(res.sum())
+    clocks = sampler.stop() if rank == 0 else {}
+
+    # ---- roofline denominator: measured DFMA issue rate (same box, same run)
+    dfma_rate, dfma_ms = gc.dfma_peak(local, 300.0)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = peak_file()
+    w_exec = workloads.W_EXEC[args.workload]
+    w_survey = workloads.W_SURVEY[args.workload]
+    pm_per_s_kernel = pm / (kernel_ms * 1e-3)
+    ach_tflops = pm_per_s_kernel * w_exec * 2 / 1e12
+    peak_tflops = dfma_rate * 2 / 1e12
+    line = {
+        "metric": METRIC, "value": world * pm / (dev_ms * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world,
+        "steps": K, "warmup": W, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {
+            "workload": workload_name(args.workload), "kind": kind, "dim": d, "modes": n,
+            "points_per_gpu": m, "point_modes_per_gpu": pm,
+            "l2": "rotating %d input/output sets (%.0f MB > 126 MB L2) so no step re-reads L2-resident data"
+                  % (n_sets, n_sets * (pos_bytes + out_bytes) / 1e6),
+            "kernel_variant": {"points_per_thread": variant["points_per_thread"],
+                               "lanes_per_point": variant["lanes_per_point"]},
+        },
+        "e2e": {"value": world * pm / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": st["h2d_bytes"], "d2h_bytes_per_step": st["d2h_bytes"],
+                "api": "gstools_core.%s(host arrays; pos pinned, result in a host ndarray)" % kind,
+                "chunks_per_step": st["n_chunks"], "checksum": checksum},
+        "gpu_launches": launches + e2e_launches,
+        "roofline": {
+            "bound": "fp64", "achieved": ach_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
+            "frac": ach_tflops / peak_tflops, "traffic": None,
+            "kernel": "gsf_sum_kernel", "kernel_ms": kernel_ms,
+            "fp64_slots_per_point_mode": w_exec,
+            "peak_source": "gsf_dfma_peak measured in this run: %.2f T DFMA/s over %.0f ms (of measured)"
+                           % (dfma_rate / 1e12, dfma_ms),
+            "frac_at_survey_work": pm_per_s_kernel * w_survey / dfma_rate,
+            "survey_slots_per_point_mode": w_survey,
+            "hbm_gbs_needed": (pos_bytes + out_bytes) / (kernel_ms * 1e-3) / 1e9,
+            "hbm_gbs_measured_peak": peaks.get("hbm_gbs"),
+        },
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        _, info, _ = cpu_reference_rate(w, args.cpu_seconds)
+        line["cpu_baseline"] = info
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -11,7 +11,7 @@
 //     s   : 1 DMUL   s = r*r
 //     u   : 6 DFMA   u = sqrt2*cos(pi/2 r), minimax deg-6 in s      (cospi_poly.cuh)
 //     y   : 1 DFMA   cos(pi r) = u*u - 1
-//     acc : NC DFMA  acc_a += (+-A_a) * y, sign = parity of n (integer XOR, not on the FP64 pipe)
+//     acc : NC DFMA  acc_a += A_a * (+-y), sign = parity of n (one integer IMAD on y's high word)
 // = D + 11 + NC FP64-pipe instructions per point*mode (15 for the 3-D scalar field).
 //
 // Mapping.  One CTA = kThreads threads = a tile of P*kThreads/L points.  A group of L lanes shares
@@ -144,28 +144,40 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 }
 
 // ------------------------------------------------------------------------------------------
-// cos(pi*t) for the reduced argument, plus the sign bit (parity of rint(t)) as a word to XOR
-// into the high half of a double.  9 FP64-pipe instructions + 1 shift.
-__device__ __forceinline__ double cospi_core(double t, uint32_t &flip)
+// The seven polynomial coefficients live in constant memory and are read ONCE per thread into
+// registers: as literals ptxas re-materialises them with UMOV pairs inside the mode loop, and
+// every non-FP64 instruction there costs an issue cycle the FP64 pipe could have used.
+struct PolyCoef {
+    double c0, c1, c2, c3, c4, c5, c6;
+};
+__constant__ double gsf_poly_u[8] = {GSF_U0, GSF_U1, GSF_U2, GSF_U3, GSF_U4, GSF_U5, GSF_U6, 0.0};
+__device__ __forceinline__ PolyCoef load_coef()
+{
+    PolyCoef c;
+    c.c0 = gsf_poly_u[0]; c.c1 = gsf_poly_u[1]; c.c2 = gsf_poly_u[2]; c.c3 = gsf_poly_u[3];
+    c.c4 = gsf_poly_u[4]; c.c5 = gsf_poly_u[5]; c.c6 = gsf_poly_u[6];
+    return c;
+}
+
+// (-1)^rint(t) * cos(pi*r): cos(pi*t) for the reduced argument with the sign applied.
+// 11 FP64-pipe instructions + 1 integer multiply-add: adding parity<<31 to the high word
+// modulo 2^32 is exactly an XOR of the sign bit.
+__device__ __forceinline__ double cospi_signed(double t, const PolyCoef &c)
 {
     const double tn = __dadd_rn(t, kMagic);     // low mantissa bits = rint(t)
     const double nf = __dadd_rn(tn, -kMagic);   // rint(t) as a double
     const double r = __dadd_rn(t, -nf);         // exact, |r| <= 1/2
     const double s = __dmul_rn(r, r);
-    double u = GSF_U6;
-    u = fma(u, s, GSF_U5);
-    u = fma(u, s, GSF_U4);
-    u = fma(u, s, GSF_U3);
-    u = fma(u, s, GSF_U2);
-    u = fma(u, s, GSF_U1);
-    u = fma(u, s, GSF_U0);
-    flip = static_cast<uint32_t>(__double2loint(tn)) << 31;
-    return fma(u, u, -1.0);
-}
-
-__device__ __forceinline__ double xor_sign(double v, uint32_t flip)
-{
-    return __hiloint2double(__double2hiint(v) ^ static_cast<int>(flip), __double2loint(v));
+    double u = fma(c.c6, s, c.c5);
+    u = fma(u, s, c.c4);
+    u = fma(u, s, c.c3);
+    u = fma(u, s, c.c2);
+    u = fma(u, s, c.c1);
+    u = fma(u, s, c.c0);
+    const double y = fma(u, u, -1.0);
+    const uint32_t hi = static_cast<uint32_t>(__double2hiint(y)) +
+                        (static_cast<uint32_t>(__double2loint(tn)) << 31);
+    return __hiloint2double(static_cast<int>(hi), __double2loint(y));
 }
 
 struct SumArgs {
@@ -212,6 +224,8 @@ __global__ void __launch_bounds__(kThreads) gsf_sum_kernel(SumArgs a)
 #pragma unroll
         for (int c = 0; c < NC; ++c) acc[p][c] = 0.0;
 
+    const PolyCoef coef = load_coef();
+
     // ---- mode ring: thread 0 is the producer
     const int64_t n_blocks = (a.n_modes + kModeBlock - 1) / kModeBlock;
     if (tid == 0) {
@@ -240,7 +254,8 @@ __global__ void __launch_bounds__(kThreads) gsf_sum_kernel(SumArgs a)
         const int cnt = (int)((a.n_modes - m0) < kModeBlock ? (a.n_modes - m0) : kModeBlock);
         const double *blk = &s_rec[st][0];
 
-#pragma unroll 2
+        constexpr int kUnroll = P >= 4 ? 2 : (P >= 2 ? 4 : 8);
+#pragma unroll kUnroll
         for (int i = sub; i < cnt; i += L) {
             const double *m = blk + i * R;
             double kh[D], nth, amp[NC];
@@ -254,15 +269,9 @@ __global__ void __launch_bounds__(kThreads) gsf_sum_kernel(SumArgs a)
                 double t = nth;
 #pragma unroll
                 for (int d = 0; d < D; ++d) t = fma(kh[d], x[p][d], t);
-                uint32_t flip;
-                const double y = cospi_core(t, flip);
-                if (NC == 1) {
-                    acc[p][0] = fma(xor_sign(amp[0], flip), y, acc[p][0]);
-                } else {
-                    const double ys = xor_sign(y, flip);
+                const double y = cospi_signed(t, coef);
 #pragma unroll
-                    for (int c = 0; c < NC; ++c) acc[p][c] = fma(amp[c], ys, acc[p][c]);
-                }
+                for (int c = 0; c < NC; ++c) acc[p][c] = fma(amp[c], y, acc[p][c]);
             }
         }
         __syncthreads();                              // everyone is done with stage st
@@ -290,7 +299,7 @@ __global__ void __launch_bounds__(kThreads) gsf_sum_kernel(SumArgs a)
 // DFMA peak micro-benchmark: kChains independent dependent-FMA chains per thread, all SMs at
 // full occupancy.  Each loop iteration issues kChains*kUnroll DFMAs and nothing else of note.
 constexpr int kPeakChains = 8;
-constexpr int kPeakUnroll = 16;
+constexpr int kPeakUnroll = 32;
 __global__ void __launch_bounds__(256) gsf_dfma_peak_kernel(double *sink, int iters, double a, double b)
 {
     double v[kPeakChains];

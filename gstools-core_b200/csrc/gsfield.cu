@@ -62,7 +62,7 @@ SumKernel pick_pl(int P, int L)
 {
 #define GSF_V(p, l) \
     if (P == p && L == l) return gsf::gsf_sum_kernel<D, NC, p, l>;
-    GSF_V(4, 1) GSF_V(2, 1) GSF_V(1, 1)
+    GSF_V(4, 1) GSF_V(3, 1) GSF_V(2, 1) GSF_V(1, 1)
     GSF_V(2, 2) GSF_V(2, 4) GSF_V(2, 8) GSF_V(2, 16) GSF_V(2, 32)
     GSF_V(1, 2) GSF_V(1, 4) GSF_V(1, 8) GSF_V(1, 16) GSF_V(1, 32)
 #undef GSF_V
@@ -293,37 +293,65 @@ int validate(const Problem &p)
     return GSF_OK;
 }
 
-// choose points-per-thread P and lanes-per-point L so the grid fills the machine
+// Resident CTAs per SM of a kernel variant (cached per function pointer).
+int variant_occupancy(SumKernel fn)
+{
+    static std::vector<std::pair<SumKernel, int>> cache;
+    for (auto &e : cache)
+        if (e.first == fn) return e.second;
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kThreads, 0) != cudaSuccess) {
+        cudaGetLastError();
+        occ = 4;
+    }
+    occ = std::max(occ, 1);
+    cache.emplace_back(fn, occ);
+    return occ;
+}
+
+// Choose points-per-thread P and lanes-per-point L for a launch of m_launch points.
+//   * L = 1 whenever the grid gives every SM at least ~2 CTAs; then P is picked from {4,3,2,1}
+//     by predicted efficiency = wave quantisation (CTAs / resident slots, rounded up) times the
+//     measured issue efficiency of that P (more points per thread amortise the LDS / loop
+//     instructions that steal issue cycles from the FP64 pipe).
+//   * small problems split the modes over L lanes of a point group so that all SMs get work.
 void choose_variant(const DeviceCtx &d, const Problem &p, int64_t m_launch, int *P, int *L)
 {
     Context &c = ctx();
-    const bool hi_dim = p.dim > 3;
-    if (c.force_p > 0 && c.force_l > 0 && pick_kernel(p.dim, p.kind == gsf::kIncompr, c.force_p, c.force_l)) {
+    const bool inc = p.kind == gsf::kIncompr;
+    if (c.force_p > 0 && c.force_l > 0 && pick_kernel(p.dim, inc, c.force_p, c.force_l)) {
         *P = c.force_p;
         *L = c.force_l;
         return;
     }
-    const int cand_l_lo[] = {1, 2, 4, 8, 16, 32};
-    const int cand_l_hi[] = {1, 4, 32};
-    const int *cl = hi_dim ? cand_l_hi : cand_l_lo;
-    const int ncl = hi_dim ? 3 : 6;
-    const int p0 = hi_dim ? 1 : 2;
-    const double slots = (double)d.sm_count * 4.0;   // ~4 resident CTAs of 128 threads per SM
-    int bestP = p0, bestL = 1;
+    if (p.dim > 3) {   // dims 4..8 ship P = 1 only
+        const int64_t ctas1 = (m_launch + kThreads - 1) / kThreads;
+        *P = 1;
+        *L = ctas1 >= 2 * d.sm_count ? 1 : (ctas1 * 4 >= 2 * d.sm_count || p.N < 256 ? 4 : 32);
+        if (p.N < 8 * *L) *L = 1;
+        return;
+    }
+    static const double base_eff[5] = {0.0, 0.86, 0.90, 0.92, 0.93};
+    int bestP = 1, bestL = 1;
     double best = -1.0;
-    for (int li = 0; li < ncl; ++li) {
-        const int l = cl[li];
-        if (l > 1 && p.N / l < 8 && li > 0) break;   // keep >= 8 modes per lane
-        const double ctas = (double)((m_launch * l + (int64_t)p0 * kThreads - 1) / ((int64_t)p0 * kThreads));
+    for (int pp = 4; pp >= 1; --pp) {
+        SumKernel fn = pick_kernel(p.dim, inc, pp, 1);
+        const double slots = (double)d.sm_count * variant_occupancy(fn);
+        const double ctas = (double)((m_launch + (int64_t)pp * kThreads - 1) / ((int64_t)pp * kThreads));
+        if (ctas < 2.0 * d.sm_count && pp > 1) continue;      // too few CTAs: try smaller P first
         const double w = ctas / slots;
-        const double eff = w >= 1.0 ? w / (double)(int64_t)(w + 0.999999) : w;
-        const double score = eff - 0.01 * li;        // prefer small L on ties
-        if (score > best) {
-            best = score;
-            bestP = p0;
-            bestL = l;
+        const double eff = (w >= 1.0 ? w / (double)(int64_t)(w + 0.999999) : 1.0) * base_eff[pp];
+        if (eff > best) {
+            best = eff;
+            bestP = pp;
         }
-        if (eff >= 0.96) break;
+    }
+    const int64_t ctas1 = (m_launch + kThreads - 1) / kThreads;   // P = 1, L = 1
+    if (ctas1 < 2 * d.sm_count) {
+        // not enough points to occupy the machine: widen with L (keep >= 8 modes per lane)
+        bestP = 1;
+        bestL = 1;
+        while (bestL < 32 && ctas1 * bestL < 2 * d.sm_count && p.N >= 16 * bestL) bestL *= 2;
     }
     *P = bestP;
     *L = bestL;

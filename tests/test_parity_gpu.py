@@ -99,7 +99,7 @@ def test_fourier_random(d):
 
 
 # ------------------------------------------------------------------------------- kernel variants
-@pytest.mark.parametrize("P,L", [(4, 1), (2, 1), (1, 1), (2, 2), (2, 4), (2, 8), (2, 16), (2, 32),
+@pytest.mark.parametrize("P,L", [(4, 1), (3, 1), (2, 1), (1, 1), (2, 2), (2, 4), (2, 8), (2, 16), (2, 32),
                                  (1, 2), (1, 4), (1, 8), (1, 16), (1, 32)])
 def test_all_variants_agree(P, L):
     k, z1, z2, pos = _rand(7, 3, 700, 3001, heavy=True)

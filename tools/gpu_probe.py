@@ -25,16 +25,29 @@ print("devices", gc.device_count(), torch.cuda.get_device_name(0))
 for ms in (50, 500, 2000):
     r, t = gc.dfma_peak(0, ms)
     print("dfma_peak min_ms=%d: %.3f T DFMA/s (%.1f ms) -> %.1f DFMA/clk/SM @1965MHz" % (ms, r / 1e12, t, r / 148 / 1.965e9))
-for cfg in ("c2", "c3", "c1"):
-    w = workloads.make(cfg)
+for cfg in ("c2", "c3", "c4s"):
+    w = workloads.make("c4", 0.0625) if cfg == "c4s" else workloads.make(cfg)
     pm = w["m"] * w["n"]
     oshape = (3, w["m"]) if cfg == "c3" else (w["m"],)
-    for P, L in [(0, 0), (4, 1), (2, 1), (1, 1), (2, 2), (2, 4), (2, 8), (1, 2), (1, 4), (1, 8), (1, 32)]:
+    for P, L in [(0, 0), (4, 1), (3, 1), (2, 1), (1, 1), (2, 2), (2, 4), (1, 4)]:
         gc.set_variant(P, L)
         ms = time_device(w["kind"], w["args"], oshape)
         s = gc.last_stats()
         print("%s P=%d L=%d (used %d,%d): %.4f ms  %.1f Gpm/s" % (cfg, P, L, s["points_per_thread"], s["lanes_per_point"], ms, pm / ms / 1e6))
     gc.set_variant(0, 0)
+# size sweep (3-D scalar, N=1000): heuristic vs forced variants
+rng = np.random.default_rng(0)
+for m in (2000, 10000, 30000, 100000, 300000, 1000000, 3000000):
+    k = rng.normal(size=(3, 1000)); z1 = rng.normal(size=1000); z2 = rng.normal(size=1000)
+    pos = rng.uniform(0, 100, size=(3, m))
+    res = []
+    for P, L in [(0, 0), (4, 1), (3, 1), (2, 1), (1, 1), (1, 4), (1, 16)]:
+        gc.set_variant(P, L)
+        ms = time_device("summate", (k, z1, z2, pos), (m,))
+        s = gc.last_stats()
+        res.append("(%d,%d)%s %.0f" % (s["points_per_thread"], s["lanes_per_point"], "*" if P == 0 else "", m * 1000 / ms / 1e6))
+    print("sweep m=%d Gpm/s:" % m, "  ".join(res))
+gc.set_variant(0, 0)
 # e2e host paths on c2
 w = workloads.make("c2")
 k, z1, z2, pos = w["args"]
