@@ -640,6 +640,14 @@ int run_shard(DeviceCtx &d, const Problem &p, int64_t j_beg, int64_t j_end, int 
     return GSF_OK;
 }
 
+// Contiguous point range of shard g of G: boundaries rounded down to multiples of 1024 points
+// (so every shard but the last starts and ends on a chunk/tile boundary), last shard takes the rest.
+void shard_bounds(int64_t m, int G, int g, int64_t *j0, int64_t *j1)
+{
+    *j0 = m * g / G / 1024 * 1024;
+    *j1 = g + 1 == G ? m : m * (g + 1) / G / 1024 * 1024;
+}
+
 std::vector<int> default_devices()
 {
     std::vector<int> v;
@@ -728,8 +736,8 @@ int run_host_call(const Problem &p)
         std::vector<std::thread> th;
         std::vector<int> Ps(G), Ls(G);
         for (int g = 0; g < G; ++g) {
-            const int64_t j0 = p.M * g / G / 1024 * 1024;
-            const int64_t j1 = g + 1 == G ? p.M : p.M * (g + 1) / G / 1024 * 1024;
+            int64_t j0, j1;
+            shard_bounds(p.M, G, g, &j0, &j1);
             th.emplace_back([&, g, j0, j1]() {
                 DeviceCtx &d = *used[g];
                 int r = run_shard(d, p, j0, j1, pos_kind, out_kind, &Ps[g], &Ls[g]);
@@ -837,6 +845,15 @@ int gsf_summate_on_stream(int kind, int dim, int64_t n_modes, int64_t n_points, 
     std::vector<DeviceCtx *> used(1, d);
     collect_stats(p, used, ms, P, L, 2, 2);
     if (prev != pd) cudaSetDevice(prev);
+    return GSF_OK;
+}
+
+int gsf_shard_bounds(int64_t n_points, int n_shards, int shard, int64_t *begin, int64_t *end)
+{
+    if (n_points < 0 || n_shards < 1 || shard < 0 || shard >= n_shards || !begin || !end)
+        return fail(GSF_ERR_ARG, "bad shard request: n_points=%lld n_shards=%d shard=%d", (long long)n_points,
+                    n_shards, shard);
+    shard_bounds(n_points, n_shards, shard, begin, end);
     return GSF_OK;
 }
 

@@ -69,6 +69,7 @@ def _load():
     L.gsf_summate_fourier.argtypes = head + a1 + a2 + a1 + a1 + a2 + [_vp, _int]
     L.gsf_summate_on_stream.argtypes = [_int] + head + a1 + a2 + a1 + a1 + a2 + [_vp, _i64, _i64, _vp]
     L.gsf_set_devices.argtypes = [ctypes.POINTER(_int), _int]
+    L.gsf_shard_bounds.argtypes = [_i64, _int, _int, ctypes.POINTER(_i64), ctypes.POINTER(_i64)]
     L.gsf_set_chunk_points.argtypes = [_i64]
     L.gsf_set_variant.argtypes = [_int, _int]
     L.gsf_set_profiling.argtypes = [_int]
@@ -77,7 +78,7 @@ def _load():
                                 ctypes.POINTER(ctypes.c_double)]
     L.gsf_last_error.restype = ctypes.c_char_p
     for name in ("gsf_summate", "gsf_summate_incompr", "gsf_summate_fourier", "gsf_summate_on_stream",
-                 "gsf_set_devices", "gsf_set_chunk_points", "gsf_set_variant", "gsf_set_profiling",
+                 "gsf_set_devices", "gsf_shard_bounds", "gsf_set_chunk_points", "gsf_set_variant", "gsf_set_profiling",
                  "gsf_get_last_stats", "gsf_dfma_peak", "gsf_abi_version", "gsf_device_count",
                  "gsf_shutdown"):
         getattr(L, name).restype = _int
@@ -275,6 +276,16 @@ def set_devices(device_ids=None):
     rc = L.gsf_set_devices(arr, len(ids))
     if rc:
         _raise(rc)
+
+
+def shard_bounds(n_points, n_shards, shard):
+    """Contiguous point range [begin, end) of one shard: the partition used across devices
+    inside one call and across ranks (one process per GPU) by bench.py. No collective needed."""
+    b, e = _i64(), _i64()
+    rc = _load().gsf_shard_bounds(int(n_points), int(n_shards), int(shard), ctypes.byref(b), ctypes.byref(e))
+    if rc:
+        _raise(rc)
+    return b.value, e.value
 
 
 def set_chunk_points(n):

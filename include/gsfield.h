@@ -121,6 +121,9 @@ int gsf_device_count(void);
 /* Devices the host-memory entry points shard points over (contiguous ranges, no collective).
  * n == 0 restores the default: env GSF_DEVICES="0,1,.." if set, else device 0 only. */
 int gsf_set_devices(const int *device_ids, int n);
+/* The contiguous point range [begin, end) that shard `shard` of `n_shards` owns -- the partition
+ * the library uses across devices and bench.py uses across ranks (one process per GPU). */
+int gsf_shard_bounds(int64_t n_points, int n_shards, int shard, int64_t *begin, int64_t *end);
 /* Points per pipeline chunk for host-resident data (0 = default). */
 int gsf_set_chunk_points(int64_t chunk_points);
 /* Force the kernel variant (0,0 = heuristic).  P in {1,2,4}, L in {1,2,4,8,16,32}. */
