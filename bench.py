@@ -155,9 +155,10 @@ def run_reference(args):
 
     w = workloads.make(args.workload, args.scale)
     threads = oracle.max_threads()
-    steps = max(1, min(args.steps, 5))
-    warm = max(1, min(args.warmup, 1))
-    per_step = max(1.0, min(20.0, 60.0 / (steps + warm)))
+    steps = max(1, args.steps)
+    warm = max(0, args.warmup)
+    # bounded sample per step: the whole run (warm-up + K steps) is sized to ~2 minutes of CPU time
+    per_step = max(0.05, min(20.0, 120.0 / (steps + warm)))
     _, info, (sub, ms, _dt) = cpu_reference_rate(w, per_step, threads)
     fn = getattr(oracle, w["kind"])
     for _ in range(warm):
