@@ -293,28 +293,13 @@ int validate(const Problem &p)
     return GSF_OK;
 }
 
-// Resident CTAs per SM of a kernel variant (cached per function pointer).
-int variant_occupancy(SumKernel fn)
-{
-    static std::vector<std::pair<SumKernel, int>> cache;
-    for (auto &e : cache)
-        if (e.first == fn) return e.second;
-    int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kThreads, 0) != cudaSuccess) {
-        cudaGetLastError();
-        occ = 4;
-    }
-    occ = std::max(occ, 1);
-    cache.emplace_back(fn, occ);
-    return occ;
-}
-
 // Choose points-per-thread P and lanes-per-point L for a launch of m_launch points.
-//   * L = 1 whenever the grid gives every SM at least ~2 CTAs; then P is picked from {4,3,2,1}
-//     by predicted efficiency = wave quantisation (CTAs / resident slots, rounded up) times the
-//     measured issue efficiency of that P (more points per thread amortise the LDS / loop
-//     instructions that steal issue cycles from the FP64 pipe).
-//   * small problems split the modes over L lanes of a point group so that all SMs get work.
+// Table from tools/variant_sweep.py on B200 (N = 1000, all kinds/dims):
+//   * below ~750k points P = 1 wins (most CTAs per SM => best balance across the 148 SMs);
+//   * above, P = 3 amortises the LDS/loop instructions that steal issue cycles from the FP64
+//     pipe (2-D scalar: P = 2 up to 2M points, P = 4 beyond);
+//   * fewer than 2 CTAs per SM: split the modes over L lanes of a point group so that every SM
+//     gets work (keep >= 16 modes per lane).
 void choose_variant(const DeviceCtx &d, const Problem &p, int64_t m_launch, int *P, int *L)
 {
     Context &c = ctx();
@@ -324,34 +309,19 @@ void choose_variant(const DeviceCtx &d, const Problem &p, int64_t m_launch, int 
         *L = c.force_l;
         return;
     }
-    if (p.dim > 3) {   // dims 4..8 ship P = 1 only
-        const int64_t ctas1 = (m_launch + kThreads - 1) / kThreads;
+    const int64_t ctas1 = (m_launch + kThreads - 1) / kThreads;   // P = 1, L = 1
+    if (p.dim > 3) {   // dims 4..8 ship P = 1 and L in {1, 4, 32}
         *P = 1;
-        *L = ctas1 >= 2 * d.sm_count ? 1 : (ctas1 * 4 >= 2 * d.sm_count || p.N < 256 ? 4 : 32);
-        if (p.N < 8 * *L) *L = 1;
+        *L = ctas1 >= 2 * d.sm_count ? 1 : (ctas1 * 4 >= 2 * d.sm_count || p.N < 512 ? 4 : 32);
+        if (p.N < 16 * *L) *L = 1;
         return;
     }
-    static const double base_eff[5] = {0.0, 0.86, 0.90, 0.92, 0.93};
     int bestP = 1, bestL = 1;
-    double best = -1.0;
-    for (int pp = 4; pp >= 1; --pp) {
-        SumKernel fn = pick_kernel(p.dim, inc, pp, 1);
-        const double slots = (double)d.sm_count * variant_occupancy(fn);
-        const double ctas = (double)((m_launch + (int64_t)pp * kThreads - 1) / ((int64_t)pp * kThreads));
-        if (ctas < 2.0 * d.sm_count && pp > 1) continue;      // too few CTAs: try smaller P first
-        const double w = ctas / slots;
-        const double eff = (w >= 1.0 ? w / (double)(int64_t)(w + 0.999999) : 1.0) * base_eff[pp];
-        if (eff > best) {
-            best = eff;
-            bestP = pp;
-        }
-    }
-    const int64_t ctas1 = (m_launch + kThreads - 1) / kThreads;   // P = 1, L = 1
-    if (ctas1 < 2 * d.sm_count) {
-        // not enough points to occupy the machine: widen with L (keep >= 8 modes per lane)
-        bestP = 1;
-        bestL = 1;
-        while (bestL < 32 && ctas1 * bestL < 2 * d.sm_count && p.N >= 16 * bestL) bestL *= 2;
+    if (m_launch >= 750000) {
+        bestP = 3;
+        if (!inc && p.dim == 2) bestP = m_launch >= 2000000 ? 4 : 2;
+    } else if (ctas1 < 2 * d.sm_count) {
+        while (bestL < 32 && ctas1 * bestL < 2 * d.sm_count && p.N >= 32 * bestL) bestL *= 2;
     }
     *P = bestP;
     *L = bestL;

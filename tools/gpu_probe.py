@@ -29,7 +29,7 @@ for cfg in ("c2", "c3", "c4s"):
     w = workloads.make("c4", 0.0625) if cfg == "c4s" else workloads.make(cfg)
     pm = w["m"] * w["n"]
     oshape = (3, w["m"]) if cfg == "c3" else (w["m"],)
-    for P, L in [(0, 0), (4, 1), (3, 1), (2, 1), (1, 1), (2, 2), (2, 4), (1, 4)]:
+    for P, L in [(0, 0), (8, 1), (6, 1), (4, 1), (3, 1), (2, 1), (1, 1)]:
         gc.set_variant(P, L)
         ms = time_device(w["kind"], w["args"], oshape)
         s = gc.last_stats()
@@ -37,11 +37,11 @@ for cfg in ("c2", "c3", "c4s"):
     gc.set_variant(0, 0)
 # size sweep (3-D scalar, N=1000): heuristic vs forced variants
 rng = np.random.default_rng(0)
-for m in (2000, 10000, 30000, 100000, 300000, 1000000, 3000000):
+for m in (10000, 100000, 300000, 1000000, 2000000, 3000000, 10000000):
     k = rng.normal(size=(3, 1000)); z1 = rng.normal(size=1000); z2 = rng.normal(size=1000)
     pos = rng.uniform(0, 100, size=(3, m))
     res = []
-    for P, L in [(0, 0), (4, 1), (3, 1), (2, 1), (1, 1), (1, 4), (1, 16)]:
+    for P, L in [(0, 0), (8, 1), (6, 1), (4, 1), (3, 1), (2, 1), (1, 1), (1, 4), (1, 16)]:
         gc.set_variant(P, L)
         ms = time_device("summate", (k, z1, z2, pos), (m,))
         s = gc.last_stats()
