@@ -18,9 +18,14 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <map>
 #include <mutex>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/gsfield.h"
@@ -272,6 +277,7 @@ struct Problem {
     const double *z2; int64_t z2s;
     const double *pos; int64_t ps0, ps1;
     double *out; int64_t os0, os1;
+    int threads_hint = 0;
     int nc() const { return kind == gsf::kIncompr ? dim : 1; }
     int rec() const { return gsf::rec_doubles(dim, nc()); }
 };
@@ -427,18 +433,115 @@ void reset_call_counters(DeviceCtx &d)
     d.err.clear();
 }
 
-// gather rows [j0, j0+cnt) of a strided (dim, M) host array into `dst` (row stride cnt)
-void gather_pos(const Problem &p, int64_t j0, int64_t cnt, double *dst)
-{
-    for (int a = 0; a < p.dim; ++a) {
-        const double *src = p.pos + a * p.ps0 + j0 * p.ps1;
-        double *row = dst + (size_t)a * cnt;
-        if (p.ps1 == 1) {
-            memcpy(row, src, (size_t)cnt * sizeof(double));
-        } else {
-            for (int64_t j = 0; j < cnt; ++j) row[j] = src[j * p.ps1];
+// ---------------------------------------------------------------------------------------------
+// Persistent host worker pool for the pageable-memory staging copies (gather into / scatter out
+// of the pinned ring).  One memcpy thread moves ~10 GB/s, a PCIe 5 x16 link ~55 GB/s, so staging
+// is what bounds the pageable path; `num_threads` of the reference signature caps the workers.
+class HostPool {
+  public:
+    ~HostPool()
+    {
+        {
+            std::lock_guard<std::mutex> l(mu_);
+            stop_ = true;
+        }
+        cv_work_.notify_all();
+        for (auto &t : workers_) t.join();
+    }
+    // run f(part) for part in [0, n_parts) on up to n_threads threads (the caller is one of them)
+    void run(int n_parts, int n_threads, const std::function<void(int)> &f)
+    {
+        if (n_parts <= 1 || n_threads <= 1) {
+            for (int i = 0; i < n_parts; ++i) f(i);
+            return;
+        }
+        std::lock_guard<std::mutex> serial(run_mu_);
+        {
+            std::lock_guard<std::mutex> l(mu_);
+            while ((int)workers_.size() < n_threads - 1) workers_.emplace_back([this]() { worker(); });
+            job_ = &f;
+            total_ = n_parts;
+            next_.store(0);
+            done_.store(0);
+            ++gen_;
+        }
+        cv_work_.notify_all();
+        drain();
+        std::unique_lock<std::mutex> l(mu_);
+        cv_done_.wait(l, [this]() { return done_.load() >= total_; });
+        job_ = nullptr;
+    }
+
+  private:
+    void drain()
+    {
+        for (;;) {
+            const int i = next_.fetch_add(1);
+            if (i >= total_) break;
+            (*job_)(i);
+            if (done_.fetch_add(1) + 1 >= total_) {
+                std::lock_guard<std::mutex> l(mu_);
+                cv_done_.notify_all();
+            }
         }
     }
+    void worker()
+    {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> l(mu_);
+                cv_work_.wait(l, [&]() { return stop_ || gen_ != seen; });
+                if (stop_) return;
+                seen = gen_;
+            }
+            drain();
+        }
+    }
+    std::mutex mu_, run_mu_;
+    std::condition_variable cv_work_, cv_done_;
+    std::vector<std::thread> workers_;
+    const std::function<void(int)> *job_ = nullptr;
+    int total_ = 0;
+    std::atomic<int> next_{0}, done_{0};
+    uint64_t gen_ = 0;
+    bool stop_ = false;
+};
+
+HostPool &host_pool()
+{
+    static HostPool *p = new HostPool();   // leaked on purpose: no join during static destruction
+    return *p;
+}
+
+int staging_threads(int hint, int n_devices)
+{
+    if (n_devices > 1) return 1;   // one staging thread per device already
+    int hw = (int)std::thread::hardware_concurrency();
+    int t = std::max(1, std::min(8, hw / 2));
+    if (hint > 0) t = std::min(t, hint);
+    return t;
+}
+
+// split [0, cnt) into parts of >= 16k points for the pool
+inline int staging_parts(int64_t cnt, int threads) { return (int)std::max<int64_t>(1, std::min<int64_t>(threads, cnt / 16384)); }
+
+// gather rows [j0, j0+cnt) of a strided (dim, M) host array into `dst` (row stride cnt)
+void gather_pos(const Problem &p, int64_t j0, int64_t cnt, double *dst, int threads)
+{
+    const int parts = staging_parts(cnt, threads);
+    host_pool().run(parts, threads, [&](int part) {
+        const int64_t b = cnt * part / parts, e = cnt * (part + 1) / parts;
+        for (int a = 0; a < p.dim; ++a) {
+            const double *src = p.pos + a * p.ps0 + (j0 + b) * p.ps1;
+            double *row = dst + (size_t)a * cnt + b;
+            if (p.ps1 == 1) {
+                memcpy(row, src, (size_t)(e - b) * sizeof(double));
+            } else {
+                for (int64_t j = 0; j < e - b; ++j) row[j] = src[j * p.ps1];
+            }
+        }
+    });
 }
 
 struct OutLayout {
@@ -447,35 +550,39 @@ struct OutLayout {
 };
 
 // scatter a finished staging-out chunk into the user's (strided) output
-void scatter_out(const Problem &p, const OutLayout &lay, int64_t j0, int64_t cnt, const double *src)
+void scatter_out(const Problem &p, const OutLayout &lay, int64_t j0, int64_t cnt, const double *src, int threads)
 {
     const int nc = p.nc();
-    if (nc == 1) {
-        if (p.os1 == 1) {
-            memcpy(p.out + j0, src, (size_t)cnt * sizeof(double));
-        } else {
-            for (int64_t j = 0; j < cnt; ++j) p.out[(j0 + j) * p.os1] = src[j];
+    const int parts = staging_parts(cnt, threads);
+    host_pool().run(parts, threads, [&](int part) {
+        const int64_t b = cnt * part / parts, e = cnt * (part + 1) / parts, n = e - b;
+        if (nc == 1) {
+            if (p.os1 == 1) {
+                memcpy(p.out + j0 + b, src + b, (size_t)n * sizeof(double));
+            } else {
+                for (int64_t j = b; j < e; ++j) p.out[(j0 + j) * p.os1] = src[j];
+            }
+            return;
         }
-        return;
-    }
-    if (lay.aos) {   // os0 == 1, os1 == nc: contiguous records
-        memcpy(p.out + j0 * p.os1, src, (size_t)cnt * nc * sizeof(double));
-        return;
-    }
-    for (int a = 0; a < nc; ++a) {
-        const double *row = src + (size_t)a * cnt;
-        double *dst = p.out + a * p.os0 + j0 * p.os1;
-        if (p.os1 == 1) {
-            memcpy(dst, row, (size_t)cnt * sizeof(double));
-        } else {
-            for (int64_t j = 0; j < cnt; ++j) dst[j * p.os1] = row[j];
+        if (lay.aos) {   // os0 == 1, os1 == nc: contiguous records
+            memcpy(p.out + (j0 + b) * p.os1, src + (size_t)b * nc, (size_t)n * nc * sizeof(double));
+            return;
         }
-    }
+        for (int a = 0; a < nc; ++a) {
+            const double *row = src + (size_t)a * cnt + b;
+            double *dst = p.out + a * p.os0 + (j0 + b) * p.os1;
+            if (p.os1 == 1) {
+                memcpy(dst, row, (size_t)n * sizeof(double));
+            } else {
+                for (int64_t j = 0; j < n; ++j) dst[j * p.os1] = row[j];
+            }
+        }
+    });
 }
 
 // Process points [j_beg, j_end) of the problem on device d (host- or device-resident pos/out).
 int run_shard(DeviceCtx &d, const Problem &p, int64_t j_beg, int64_t j_end, int pos_kind, int out_kind,
-              int *P_used, int *L_used)
+              int *P_used, int *L_used, int host_threads)
 {
     GSF_CUDA(cudaSetDevice(d.dev));
     reset_call_counters(d);
@@ -495,7 +602,7 @@ int run_shard(DeviceCtx &d, const Problem &p, int64_t j_beg, int64_t j_end, int 
     if (!(pos_dev && out_dev)) {
         chunk = ctx().chunk_points;
         if (chunk <= 0) {
-            chunk = (m_shard + 7) / 8;
+            chunk = (m_shard + 15) / 16;
             chunk = std::max<int64_t>(chunk, 1 << 15);
             chunk = std::min<int64_t>(chunk, 1 << 20);
         }
@@ -527,7 +634,7 @@ int run_shard(DeviceCtx &d, const Problem &p, int64_t j_beg, int64_t j_end, int 
         // drain the staging-out buffer of the chunk that used this slot last
         if (pend[si].live) {
             GSF_CUDA(cudaEventSynchronize(sl.ev_done));
-            scatter_out(p, lay, pend[si].j0, pend[si].cnt, sl.h_out);
+            scatter_out(p, lay, pend[si].j0, pend[si].cnt, sl.h_out, host_threads);
             pend[si].live = false;
         }
 
@@ -547,7 +654,7 @@ int run_shard(DeviceCtx &d, const Problem &p, int64_t j_beg, int64_t j_end, int 
             } else {
                 if ((rc = ensure_cap(&sl.h_pos, &sl.h_pos_cap, (size_t)p.dim * cnt, true))) return rc;
                 if (slot_in_used[si]) GSF_CUDA(cudaEventSynchronize(sl.ev_h2d));
-                gather_pos(p, j0, cnt, sl.h_pos);
+                gather_pos(p, j0, cnt, sl.h_pos, host_threads);
                 GSF_CUDA(cudaMemcpyAsync(sl.d_pos, sl.h_pos, (size_t)p.dim * cnt * sizeof(double),
                                          cudaMemcpyHostToDevice, st));
                 GSF_CUDA(cudaEventRecord(sl.ev_h2d, st));
@@ -601,7 +708,7 @@ int run_shard(DeviceCtx &d, const Problem &p, int64_t j_beg, int64_t j_end, int 
         const int si = (int)(c % kSlots);
         if (pend[si].live) {
             GSF_CUDA(cudaEventSynchronize(d.slot[si].ev_done));
-            scatter_out(p, lay, pend[si].j0, pend[si].cnt, d.slot[si].h_out);
+            scatter_out(p, lay, pend[si].j0, pend[si].cnt, d.slot[si].h_out, host_threads);
             pend[si].live = false;
         }
     }
@@ -616,6 +723,81 @@ void shard_bounds(int64_t m, int G, int g, int64_t *j0, int64_t *j1)
 {
     *j0 = m * g / G / 1024 * 1024;
     *j1 = g + 1 == G ? m : m * (g + 1) / G / 1024 * 1024;
+}
+
+// Caching allocator for pinned host memory handed to callers (result arrays): D2H then lands
+// directly in the array the caller sees, with no staging copy.  cudaMallocHost costs ~0.5 ms/MB,
+// so freed blocks are kept (up to GSF_PINNED_CACHE_MB, default 2048) and reused.
+class PinnedPool {
+  public:
+    int alloc(size_t bytes, void **out)
+    {
+        const size_t sz = (bytes + 65535) / 65536 * 65536;
+        {
+            std::lock_guard<std::mutex> l(mu_);
+            auto it = free_.lower_bound(sz);
+            if (it != free_.end() && it->first <= 2 * sz) {
+                *out = it->second;
+                live_[it->second] = it->first;
+                cached_ -= it->first;
+                free_.erase(it);
+                return GSF_OK;
+            }
+        }
+        void *p = nullptr;
+        cudaError_t e = cudaMallocHost(&p, sz);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(e == cudaErrorMemoryAllocation ? GSF_ERR_ALLOC : GSF_ERR_NO_DEVICE,
+                        "cudaMallocHost(%zu) failed: %s", sz, cudaGetErrorString(e));
+        }
+        std::lock_guard<std::mutex> l(mu_);
+        live_[p] = sz;
+        *out = p;
+        return GSF_OK;
+    }
+    int release(void *p)
+    {
+        size_t sz = 0;
+        {
+            std::lock_guard<std::mutex> l(mu_);
+            auto it = live_.find(p);
+            if (it == live_.end()) return fail(GSF_ERR_ARG, "gsf_host_free: unknown pointer");
+            sz = it->second;
+            live_.erase(it);
+            if (cached_ + sz <= cap()) {
+                free_.emplace(sz, p);
+                cached_ += sz;
+                return GSF_OK;
+            }
+        }
+        cudaFreeHost(p);
+        return GSF_OK;
+    }
+    void trim()
+    {
+        std::lock_guard<std::mutex> l(mu_);
+        for (auto &kv : free_) cudaFreeHost(kv.second);
+        free_.clear();
+        cached_ = 0;
+    }
+
+  private:
+    static size_t cap()
+    {
+        const char *e = getenv("GSF_PINNED_CACHE_MB");
+        return (size_t)(e && *e ? atoll(e) : 2048) << 20;
+    }
+    std::mutex mu_;
+    std::multimap<size_t, void *> free_;
+    std::unordered_map<void *, size_t> live_;
+    size_t cached_ = 0;
+};
+
+PinnedPool &pinned_pool()
+{
+    static PinnedPool *p = new PinnedPool();
+    return *p;
 }
 
 std::vector<int> default_devices()
@@ -701,7 +883,7 @@ int run_host_call(const Problem &p)
 
     int P = 0, L = 0;
     if (G == 1) {
-        rc = run_shard(*used[0], p, 0, p.M, pos_kind, out_kind, &P, &L);
+        rc = run_shard(*used[0], p, 0, p.M, pos_kind, out_kind, &P, &L, staging_threads(p.threads_hint, 1));
     } else {
         std::vector<std::thread> th;
         std::vector<int> Ps(G), Ls(G);
@@ -710,7 +892,7 @@ int run_host_call(const Problem &p)
             shard_bounds(p.M, G, g, &j0, &j1);
             th.emplace_back([&, g, j0, j1]() {
                 DeviceCtx &d = *used[g];
-                int r = run_shard(d, p, j0, j1, pos_kind, out_kind, &Ps[g], &Ls[g]);
+                int r = run_shard(d, p, j0, j1, pos_kind, out_kind, &Ps[g], &Ls[g], 1);
                 d.status = r;
                 if (r) d.err = g_err;   // g_err is thread-local to the worker
             });
@@ -745,9 +927,9 @@ int gsf_summate(int dim, int64_t n_modes, int64_t n_points, const double *cov_sa
                 int64_t cov_s1, const double *z1, int64_t z1_s, const double *z2, int64_t z2_s,
                 const double *pos, int64_t pos_s0, int64_t pos_s1, double *out, int num_threads)
 {
-    (void)num_threads;
     Problem p{gsf::kScalar, dim, n_modes, n_points, nullptr, 0, cov_samples, cov_s0, cov_s1, z1, z1_s,
               z2, z2_s, pos, pos_s0, pos_s1, out, 0, 1};
+    p.threads_hint = num_threads;
     return run_host_call(p);
 }
 
@@ -756,9 +938,9 @@ int gsf_summate_incompr(int dim, int64_t n_modes, int64_t n_points, const double
                         int64_t z2_s, const double *pos, int64_t pos_s0, int64_t pos_s1, double *out,
                         int64_t out_s0, int64_t out_s1, int num_threads)
 {
-    (void)num_threads;
     Problem p{gsf::kIncompr, dim, n_modes, n_points, nullptr, 0, cov_samples, cov_s0, cov_s1, z1, z1_s,
               z2, z2_s, pos, pos_s0, pos_s1, out, out_s0, out_s1};
+    p.threads_hint = num_threads;
     return run_host_call(p);
 }
 
@@ -767,9 +949,9 @@ int gsf_summate_fourier(int dim, int64_t n_modes, int64_t n_points, const double
                         const double *z1, int64_t z1_s, const double *z2, int64_t z2_s, const double *pos,
                         int64_t pos_s0, int64_t pos_s1, double *out, int num_threads)
 {
-    (void)num_threads;
     Problem p{gsf::kFourier, dim, n_modes, n_points, spectrum_factor, sf_s, modes, modes_s0, modes_s1,
               z1, z1_s, z2, z2_s, pos, pos_s0, pos_s1, out, 0, 1};
+    p.threads_hint = num_threads;
     return run_host_call(p);
 }
 
@@ -816,6 +998,18 @@ int gsf_summate_on_stream(int kind, int dim, int64_t n_modes, int64_t n_points, 
     collect_stats(p, used, ms, P, L, 2, 2);
     if (prev != pd) cudaSetDevice(prev);
     return GSF_OK;
+}
+
+int gsf_host_alloc(int64_t bytes, void **ptr)
+{
+    if (bytes <= 0 || !ptr) return fail(GSF_ERR_ARG, "gsf_host_alloc: bad arguments");
+    return pinned_pool().alloc((size_t)bytes, ptr);
+}
+
+int gsf_host_free(void *ptr)
+{
+    if (!ptr) return GSF_OK;
+    return pinned_pool().release(ptr);
 }
 
 int gsf_shard_bounds(int64_t n_points, int n_shards, int shard, int64_t *begin, int64_t *end)
@@ -921,6 +1115,7 @@ int gsf_shutdown(void)
     std::lock_guard<std::mutex> lock(c.mu);
     for (DeviceCtx *d : c.dctx) free_device_ctx(d);
     c.dctx.clear();
+    pinned_pool().trim();
     c.last = gsf_stats{};
     c.last_devs.clear();
     return GSF_OK;

@@ -22,6 +22,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import weakref
 
 import numpy as np
 
@@ -70,6 +71,8 @@ def _load():
     L.gsf_summate_on_stream.argtypes = [_int] + head + a1 + a2 + a1 + a1 + a2 + [_vp, _i64, _i64, _vp]
     L.gsf_set_devices.argtypes = [ctypes.POINTER(_int), _int]
     L.gsf_shard_bounds.argtypes = [_i64, _int, _int, ctypes.POINTER(_i64), ctypes.POINTER(_i64)]
+    L.gsf_host_alloc.argtypes = [_i64, ctypes.POINTER(_vp)]
+    L.gsf_host_free.argtypes = [_vp]
     L.gsf_set_chunk_points.argtypes = [_i64]
     L.gsf_set_variant.argtypes = [_int, _int]
     L.gsf_set_profiling.argtypes = [_int]
@@ -78,7 +81,7 @@ def _load():
                                 ctypes.POINTER(ctypes.c_double)]
     L.gsf_last_error.restype = ctypes.c_char_p
     for name in ("gsf_summate", "gsf_summate_incompr", "gsf_summate_fourier", "gsf_summate_on_stream",
-                 "gsf_set_devices", "gsf_shard_bounds", "gsf_set_chunk_points", "gsf_set_variant", "gsf_set_profiling",
+                 "gsf_set_devices", "gsf_shard_bounds", "gsf_host_alloc", "gsf_host_free", "gsf_set_chunk_points", "gsf_set_variant", "gsf_set_profiling",
                  "gsf_get_last_stats", "gsf_dfma_peak", "gsf_abi_version", "gsf_device_count",
                  "gsf_shutdown"):
         getattr(L, name).restype = _int
@@ -139,6 +142,30 @@ class _Arr:
         return (self.ptr,) + self.strides
 
 
+_PINNED_MIN = 256 * 1024          # below this a staging copy is cheaper than a pool round trip
+_PINNED_MAX = 1 << 30
+
+
+def _result_array(shape, order="C"):
+    """Freshly allocated float64 result, like the reference's owned Array1/Array2 handed to numpy
+    (src/lib.rs:47).  Mid-sized results are backed by pinned memory from the library's caching
+    pool so the device->host copy lands in them directly; the block returns to the pool when the
+    array (and every view of it) is garbage collected.  GSF_PINNED_OUTPUT=0 disables this."""
+    n = 1
+    for s in shape:
+        n *= int(s)
+    nbytes = n * 8
+    if not (_PINNED_MIN <= nbytes <= _PINNED_MAX) or os.environ.get("GSF_PINNED_OUTPUT", "1") == "0":
+        return np.empty(shape, dtype=np.float64, order=order)
+    L = _load()
+    ptr = _vp()
+    if L.gsf_host_alloc(nbytes, ctypes.byref(ptr)) != 0 or not ptr.value:
+        return np.empty(shape, dtype=np.float64, order=order)
+    buf = (ctypes.c_char * nbytes).from_address(ptr.value)
+    weakref.finalize(buf, L.gsf_host_free, ptr.value)
+    return np.frombuffer(buf, dtype=np.float64).reshape(shape, order=order)
+
+
 def _threads(num_threads):
     if num_threads is None:
         return 0
@@ -166,7 +193,7 @@ def summate(cov_samples, z1, z2, pos, num_threads=None):
         raise TypeError("summate: pos is a device array; use summate_device(..., out=...)")
     d, n = cov.shape
     m = p.shape[1]
-    out = np.empty(m, dtype=np.float64)
+    out = _result_array((m,))
     rc = L.gsf_summate(d, n, m, *cov.args(), *a1.args(), *a2.args(), *p.args(), out.ctypes.data,
                        _threads(num_threads))
     if rc:
@@ -185,7 +212,7 @@ def summate_incompr(cov_samples, z1, z2, pos, num_threads=None):
         raise TypeError("summate_incompr: pos is a device array; use summate_incompr_device(..., out=...)")
     d, n = cov.shape
     m = p.shape[1]
-    out = np.empty((d, m), dtype=np.float64, order="F")
+    out = _result_array((d, m), order="F")
     rc = L.gsf_summate_incompr(d, n, m, *cov.args(), *a1.args(), *a2.args(), *p.args(), out.ctypes.data,
                                out.strides[0] // 8, out.strides[1] // 8, _threads(num_threads))
     if rc:
@@ -206,7 +233,7 @@ def summate_fourier(spectrum_factor, modes, z1, z2, pos, num_threads=None):
         raise TypeError("summate_fourier: pos is a device array; use summate_fourier_device(..., out=...)")
     d, n = cov.shape
     m = p.shape[1]
-    out = np.empty(m, dtype=np.float64)
+    out = _result_array((m,))
     rc = L.gsf_summate_fourier(d, n, m, *sf.args(), *cov.args(), *a1.args(), *a2.args(), *p.args(),
                                out.ctypes.data, _threads(num_threads))
     if rc:

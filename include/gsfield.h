@@ -18,7 +18,8 @@
  *     library detects which (cudaPointerGetAttributes).  Host data is streamed through the GPU in
  *     chunks (H2D / kernel / D2H overlapped); device-resident data is processed in place.
  *   - `num_threads` is accepted for signature compatibility with the reference (src/field.rs:42);
- *     it never affects results.  <= 0 means "default".
+ *     it never affects results and only caps the host threads used for staging copies of
+ *     pageable memory.  <= 0 means "default".
  *   - Return value: GSF_OK or an error code; gsf_last_error() gives a thread-local message.  The
  *     library never aborts and never throws across the ABI (the reference panics => abort,
  *     Cargo.toml:22; a Rust shim turns a non-zero status back into panic!).
@@ -121,6 +122,10 @@ int gsf_device_count(void);
 /* Devices the host-memory entry points shard points over (contiguous ranges, no collective).
  * n == 0 restores the default: env GSF_DEVICES="0,1,.." if set, else device 0 only. */
 int gsf_set_devices(const int *device_ids, int n);
+/* Pinned (page-locked) host memory from a caching pool, for result arrays: a D2H into such a
+ * buffer needs no staging copy.  gsf_host_free returns the block to the pool. */
+int gsf_host_alloc(int64_t bytes, void **ptr);
+int gsf_host_free(void *ptr);
 /* The contiguous point range [begin, end) that shard `shard` of `n_shards` owns -- the partition
  * the library uses across devices and bench.py uses across ranks (one process per GPU). */
 int gsf_shard_bounds(int64_t n_points, int n_shards, int shard, int64_t *begin, int64_t *end);
