@@ -51,6 +51,7 @@ struct PrepArgs {
     int64_t n_modes;
     int dim;
     int incompr;                            // NC = dim if set, else 1
+    double scale;                           // folded into the amplitudes (fused post-scale, 8 f1)
 };
 
 // x * (1/pi) with 1/pi carried as a double-double: the result is the correctly rounded quotient
@@ -76,6 +77,7 @@ __global__ void gsf_prep_modes(PrepArgs a)
     double amp = hypot(z1, z2);
     const double th = div_pi(atan2(z2, z1));
     if (a.sf) amp = __dmul_rn(a.sf[i * a.sfs], amp);   // src/field.rs:243
+    if (a.scale != 1.0) amp = __dmul_rn(amp, a.scale);
 
     double kk = 0.0;
     for (int d = 0; d < D; ++d) {
@@ -188,6 +190,7 @@ struct SumArgs {
     int64_t n_points;
     double *out;                  // out[a*os0 + j*os1]
     int64_t os0, os1;
+    double offset[3];             // added once per output component (fused post-offset)
 };
 
 // D: spatial dimension; NC: accumulators per point (1 scalar/fourier, D incompr);
@@ -222,7 +225,7 @@ __global__ void __launch_bounds__(kThreads) gsf_sum_kernel(SumArgs a)
 #pragma unroll
     for (int p = 0; p < P; ++p)
 #pragma unroll
-        for (int c = 0; c < NC; ++c) acc[p][c] = 0.0;
+        for (int c = 0; c < NC; ++c) acc[p][c] = sub == 0 ? a.offset[c < 3 ? c : 0] : 0.0;
 
     const PolyCoef coef = load_coef();
 

@@ -30,6 +30,7 @@
 
 #include "../../include/gsfield.h"
 #include "gsf_kernels.cuh"
+#include "gsf_grid_kernels.cuh"
 
 namespace {
 
@@ -113,6 +114,8 @@ struct Slot {
     double *d_pos = nullptr, *d_out = nullptr;
     double *h_pos = nullptr, *h_out = nullptr;
     size_t d_pos_cap = 0, d_out_cap = 0, h_pos_cap = 0, h_out_cap = 0;   // in doubles
+    double *g_partial = nullptr, *g_counter = nullptr;                   // grid path: split-K workspace
+    size_t g_partial_cap = 0, g_counter_cap = 0;
 };
 
 struct DeviceCtx {
@@ -125,6 +128,8 @@ struct DeviceCtx {
     bool ws_used = false;
     double *d_raw = nullptr, *d_rec = nullptr;
     size_t raw_cap = 0, rec_cap = 0;
+    double *g_axes = nullptr, *g_E0 = nullptr, *g_E1 = nullptr, *g_F = nullptr;   // grid-path tables
+    size_t g_axes_cap = 0, g_E0_cap = 0, g_E1_cap = 0, g_F_cap = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof;   // pool of timing events
     size_t prof_used = 0;
     cudaEvent_t prep_beg = nullptr, prep_end = nullptr;
@@ -144,6 +149,7 @@ struct Context {
     int64_t chunk_points = 0;
     int force_p = 0, force_l = 0;
     bool profiling = false;
+    int grid_detect = -1;                // -1: env GSF_GRID_DETECT (default on), 0 off, 1 on
     gsf_stats last{};
     std::vector<int> last_devs;
 };
@@ -228,12 +234,18 @@ void free_device_ctx(DeviceCtx *d)
             if (sl.d_out) cudaFree(sl.d_out);
             if (sl.h_pos) cudaFreeHost(sl.h_pos);
             if (sl.h_out) cudaFreeHost(sl.h_out);
+            if (sl.g_partial) cudaFree(sl.g_partial);
+            if (sl.g_counter) cudaFree(sl.g_counter);
             if (sl.ev_h2d) cudaEventDestroy(sl.ev_h2d);
             if (sl.ev_done) cudaEventDestroy(sl.ev_done);
             if (sl.stream) cudaStreamDestroy(sl.stream);
         }
         if (d->d_raw) cudaFree(d->d_raw);
         if (d->d_rec) cudaFree(d->d_rec);
+        if (d->g_axes) cudaFree(d->g_axes);
+        if (d->g_E0) cudaFree(d->g_E0);
+        if (d->g_E1) cudaFree(d->g_E1);
+        if (d->g_F) cudaFree(d->g_F);
         for (auto &pr : d->prof) {
             cudaEventDestroy(pr.first);
             cudaEventDestroy(pr.second);
@@ -278,6 +290,8 @@ struct Problem {
     const double *pos; int64_t ps0, ps1;
     double *out; int64_t os0, os1;
     int threads_hint = 0;
+    double scale = 1.0;                  // out = scale * sum + offset[a]   
+    double offset[3] = {0.0, 0.0, 0.0};
     int nc() const { return kind == gsf::kIncompr ? dim : 1; }
     int rec() const { return gsf::rec_doubles(dim, nc()); }
 };
@@ -344,6 +358,7 @@ int launch_sum(DeviceCtx &d, const Problem &p, const double *kpos, int64_t ps0, 
     a.pos = kpos; a.ps0 = ps0; a.ps1 = ps1;
     a.n_points = m;
     a.out = kout; a.os0 = os0; a.os1 = os1;
+    for (int c = 0; c < 3; ++c) a.offset[c] = p.offset[c];
     const int64_t tile = (int64_t)P * (kThreads / L);
     const int64_t grid = (m + tile - 1) / tile;
     if (grid > 0x7fffffffLL) return fail(GSF_ERR_SHAPE, "chunk of %lld points is too large for one launch", (long long)m);
@@ -390,6 +405,7 @@ int prepare_modes(DeviceCtx &d, const Problem &p, cudaStream_t st)
     a.n_modes = N;
     a.dim = p.dim;
     a.incompr = p.kind == gsf::kIncompr;
+    a.scale = p.scale;
     a.rec = d.d_rec;
     if (all_dev) {
         if (kd != d.dev) return fail(GSF_ERR_ARG, "mode arrays live on device %d, work runs on device %d", kd, d.dev);
@@ -725,6 +741,8 @@ void shard_bounds(int64_t m, int G, int g, int64_t *j0, int64_t *j1)
     *j1 = g + 1 == G ? m : m * (g + 1) / G / 1024 * 1024;
 }
 
+#include "gsf_grid_host.inc"
+
 // Caching allocator for pinned host memory handed to callers (result arrays): D2H then lands
 // directly in the array the caller sees, with no staging copy.  cudaMallocHost costs ~0.5 ms/MB,
 // so freed blocks are kept (up to GSF_PINNED_CACHE_MB, default 2048) and reused.
@@ -819,7 +837,7 @@ std::vector<int> default_devices()
 }
 
 void collect_stats(const Problem &p, const std::vector<DeviceCtx *> &used, double total_ms, int P, int L,
-                   int pos_kind, int out_kind)
+                   int pos_kind, int out_kind, int grid_path)
 {
     Context &c = ctx();
     gsf_stats s{};
@@ -829,6 +847,7 @@ void collect_stats(const Problem &p, const std::vector<DeviceCtx *> &used, doubl
     s.lanes_per_point = L;
     s.pos_memory = pos_kind;
     s.out_memory = out_kind;
+    s.grid_path = grid_path;
     s.n_devices = (int)used.size();
     c.last_devs.clear();
     for (DeviceCtx *d : used) {
@@ -843,10 +862,28 @@ void collect_stats(const Problem &p, const std::vector<DeviceCtx *> &used, doubl
     c.last = s;
 }
 
-int run_host_call(const Problem &p)
+bool grid_detection_enabled()
+{
+    Context &c = ctx();
+    if (c.grid_detect >= 0) return c.grid_detect != 0;
+    const char *e = getenv("GSF_GRID_DETECT");
+    return !(e && e[0] == '0');
+}
+
+// `grid` != nullptr: the caller gave axis vectors (explicit structured-grid request, p.pos unused).
+int run_host_call(Problem p, const GridSpec *grid)
 {
     Context &c = ctx();
     std::lock_guard<std::mutex> lock(c.mu);
+    if (grid) {
+        if (grid->dim != 2 && grid->dim != 3)
+            return fail(GSF_ERR_DIM, "structured-grid path supports dim 2 and 3 (dim=%d)", grid->dim);
+        p.dim = grid->dim;
+        p.M = grid->points();
+        for (int a = 0; a < grid->dim; ++a)
+            if (grid->n[a] < 1 || !grid->axis[a]) return fail(GSF_ERR_SHAPE, "bad grid axis %d", a);
+        p.pos = grid->axis[0];   // placeholder so validate() sees a non-NULL pointer
+    }
     int rc = validate(p);
     if (rc) return rc;
     const int ndev_visible = device_count_raw();
@@ -858,9 +895,16 @@ int run_host_call(const Problem &p)
     }
     const auto t0 = std::chrono::steady_clock::now();
 
-    int pos_kind, pos_dev, out_kind, out_dev;
-    classify(p.pos, &pos_kind, &pos_dev);
+    int pos_kind = 0, pos_dev = -1, out_kind, out_dev;
+    if (!grid) classify(p.pos, &pos_kind, &pos_dev);
     classify(p.out, &out_kind, &out_dev);
+    if (grid) {
+        for (int a = 0; a < grid->dim; ++a) {
+            int k, dv;
+            classify(grid->axis[a], &k, &dv);
+            if (k == 2) return fail(GSF_ERR_ARG, "grid axis vectors must be host-resident");
+        }
+    }
 
     std::vector<int> devs = c.devices_explicit ? c.devices : default_devices();
     for (int id : devs)
@@ -881,9 +925,40 @@ int run_host_call(const Problem &p)
     for (int g = 0; g < G; ++g)
         if ((rc = get_device_ctx(devs[g], &used[g]))) return rc;
 
+    // ---- structured grid?  explicit request, or exact auto-detection on host-resident positions
+    GridSpec detected;
+    const GridSpec *gs = grid;
+    const int threads1 = staging_threads(p.threads_hint, 1);
+    if (!gs && pos_kind != 2 && p.N >= 32 && grid_detection_enabled() &&
+        detect_grid_host(p, &detected, threads1) && detected.rows() >= 16)
+        gs = &detected;
+
     int P = 0, L = 0;
-    if (G == 1) {
-        rc = run_shard(*used[0], p, 0, p.M, pos_kind, out_kind, &P, &L, staging_threads(p.threads_hint, 1));
+    if (gs) {
+        const int64_t R = gs->rows();
+        if (G == 1) {
+            rc = run_grid(*used[0], p, *gs, 0, R, out_kind, threads1);
+        } else {
+            std::vector<std::thread> th;
+            for (int g = 0; g < G; ++g) {
+                const int64_t r0 = R * g / G / 32 * 32;
+                const int64_t r1 = g + 1 == G ? R : R * (g + 1) / G / 32 * 32;
+                th.emplace_back([&, g, r0, r1]() {
+                    DeviceCtx &d = *used[g];
+                    int r = run_grid(d, p, *gs, r0, r1, out_kind, 1);
+                    d.status = r;
+                    if (r) d.err = g_err;
+                });
+            }
+            for (auto &t : th) t.join();
+            for (int g = 0; g < G; ++g)
+                if (used[g]->status && !rc) {
+                    rc = used[g]->status;
+                    g_err = used[g]->err;
+                }
+        }
+    } else if (G == 1) {
+        rc = run_shard(*used[0], p, 0, p.M, pos_kind, out_kind, &P, &L, threads1);
     } else {
         std::vector<std::thread> th;
         std::vector<int> Ps(G), Ls(G);
@@ -908,7 +983,7 @@ int run_host_call(const Problem &p)
     }
     if (rc) return rc;
     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    collect_stats(p, used, ms, P, L, pos_kind, out_kind);
+    collect_stats(p, used, ms, P, L, pos_kind, out_kind, gs ? (grid ? 2 : 1) : 0);
     return GSF_OK;
 }
 
@@ -930,7 +1005,7 @@ int gsf_summate(int dim, int64_t n_modes, int64_t n_points, const double *cov_sa
     Problem p{gsf::kScalar, dim, n_modes, n_points, nullptr, 0, cov_samples, cov_s0, cov_s1, z1, z1_s,
               z2, z2_s, pos, pos_s0, pos_s1, out, 0, 1};
     p.threads_hint = num_threads;
-    return run_host_call(p);
+    return run_host_call(p, nullptr);
 }
 
 int gsf_summate_incompr(int dim, int64_t n_modes, int64_t n_points, const double *cov_samples,
@@ -941,7 +1016,7 @@ int gsf_summate_incompr(int dim, int64_t n_modes, int64_t n_points, const double
     Problem p{gsf::kIncompr, dim, n_modes, n_points, nullptr, 0, cov_samples, cov_s0, cov_s1, z1, z1_s,
               z2, z2_s, pos, pos_s0, pos_s1, out, out_s0, out_s1};
     p.threads_hint = num_threads;
-    return run_host_call(p);
+    return run_host_call(p, nullptr);
 }
 
 int gsf_summate_fourier(int dim, int64_t n_modes, int64_t n_points, const double *spectrum_factor,
@@ -952,7 +1027,7 @@ int gsf_summate_fourier(int dim, int64_t n_modes, int64_t n_points, const double
     Problem p{gsf::kFourier, dim, n_modes, n_points, spectrum_factor, sf_s, modes, modes_s0, modes_s1,
               z1, z1_s, z2, z2_s, pos, pos_s0, pos_s1, out, 0, 1};
     p.threads_hint = num_threads;
-    return run_host_call(p);
+    return run_host_call(p, nullptr);
 }
 
 int gsf_summate_on_stream(int kind, int dim, int64_t n_modes, int64_t n_points, const double *spectrum_factor,
@@ -995,8 +1070,42 @@ int gsf_summate_on_stream(int kind, int dim, int64_t n_modes, int64_t n_points, 
     d->chunks = 1;
     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     std::vector<DeviceCtx *> used(1, d);
-    collect_stats(p, used, ms, P, L, 2, 2);
+    collect_stats(p, used, ms, P, L, 2, 2, 0);
     if (prev != pd) cudaSetDevice(prev);
+    return GSF_OK;
+}
+
+int gsf_summate_ex(const gsf_request *r)
+{
+    if (!r || r->struct_size != (int32_t)sizeof(gsf_request))
+        return fail(GSF_ERR_ARG, "gsf_summate_ex: NULL request or struct_size mismatch (ABI %d)", GSF_ABI_VERSION);
+    if (r->kind < 0 || r->kind > 2) return fail(GSF_ERR_ARG, "kind must be 0, 1 or 2");
+    Problem p{r->kind, r->dim, r->n_modes, r->n_points, r->spectrum_factor, r->sf_s, r->modes, r->modes_s0,
+              r->modes_s1, r->z1, r->z1_s, r->z2, r->z2_s, r->pos, r->pos_s0, r->pos_s1, r->out, r->out_s0,
+              r->out_s1};
+    if (r->kind != gsf::kIncompr) { p.os0 = 0; p.os1 = r->out_s1 ? r->out_s1 : 1; }
+    p.threads_hint = r->num_threads;
+    p.scale = r->scale;
+    for (int a = 0; a < 3; ++a) p.offset[a] = r->offset[a];
+    if (r->n_axes > 0) {
+        if (r->n_axes != r->dim) return fail(GSF_ERR_SHAPE, "n_axes (%d) must equal dim (%d)", r->n_axes, r->dim);
+        GridSpec g;
+        g.dim = r->dim;
+        for (int a = 0; a < r->dim && a < 3; ++a) {
+            g.axis[a] = r->axis[a];
+            g.n[a] = r->axis_n[a];
+            g.s[a] = r->axis_s[a] ? r->axis_s[a] : 1;
+        }
+        return run_host_call(p, &g);
+    }
+    return run_host_call(p, nullptr);
+}
+
+int gsf_set_grid_detection(int enabled)
+{
+    Context &c = ctx();
+    std::lock_guard<std::mutex> lock(c.mu);
+    c.grid_detect = enabled < 0 ? -1 : (enabled != 0);
     return GSF_OK;
 }
 

@@ -42,11 +42,29 @@ class GsfStats(ctypes.Structure):
         ("point_modes", _i64), ("h2d_bytes", _i64), ("d2h_bytes", _i64),
         ("kernel_launches", ctypes.c_int32), ("n_devices", ctypes.c_int32), ("n_chunks", ctypes.c_int32),
         ("points_per_thread", ctypes.c_int32), ("lanes_per_point", ctypes.c_int32),
-        ("pos_memory", ctypes.c_int32), ("out_memory", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("pos_memory", ctypes.c_int32), ("out_memory", ctypes.c_int32), ("grid_path", ctypes.c_int32),
     ]
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class GsfRequest(ctypes.Structure):
+    """mirror of gsf_request (include/gsfield.h)"""
+    _fields_ = [
+        ("struct_size", ctypes.c_int32), ("kind", ctypes.c_int32), ("dim", ctypes.c_int32),
+        ("num_threads", ctypes.c_int32),
+        ("n_modes", _i64), ("n_points", _i64),
+        ("spectrum_factor", _vp), ("sf_s", _i64),
+        ("modes", _vp), ("modes_s0", _i64), ("modes_s1", _i64),
+        ("z1", _vp), ("z1_s", _i64),
+        ("z2", _vp), ("z2_s", _i64),
+        ("pos", _vp), ("pos_s0", _i64), ("pos_s1", _i64),
+        ("out", _vp), ("out_s0", _i64), ("out_s1", _i64),
+        ("scale", ctypes.c_double), ("offset", ctypes.c_double * 3),
+        ("n_axes", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("axis", _vp * 3), ("axis_n", _i64 * 3), ("axis_s", _i64 * 3),
+    ]
 
 
 _lib = None
@@ -68,6 +86,8 @@ def _load():
     L.gsf_summate.argtypes = head + a2 + a1 + a1 + a2 + [_vp, _int]
     L.gsf_summate_incompr.argtypes = head + a2 + a1 + a1 + a2 + [_vp, _i64, _i64, _int]
     L.gsf_summate_fourier.argtypes = head + a1 + a2 + a1 + a1 + a2 + [_vp, _int]
+    L.gsf_summate_ex.argtypes = [ctypes.POINTER(GsfRequest)]
+    L.gsf_set_grid_detection.argtypes = [_int]
     L.gsf_summate_on_stream.argtypes = [_int] + head + a1 + a2 + a1 + a1 + a2 + [_vp, _i64, _i64, _vp]
     L.gsf_set_devices.argtypes = [ctypes.POINTER(_int), _int]
     L.gsf_shard_bounds.argtypes = [_i64, _int, _int, ctypes.POINTER(_i64), ctypes.POINTER(_i64)]
@@ -81,6 +101,7 @@ def _load():
                                 ctypes.POINTER(ctypes.c_double)]
     L.gsf_last_error.restype = ctypes.c_char_p
     for name in ("gsf_summate", "gsf_summate_incompr", "gsf_summate_fourier", "gsf_summate_on_stream",
+                 "gsf_summate_ex", "gsf_set_grid_detection",
                  "gsf_set_devices", "gsf_shard_bounds", "gsf_host_alloc", "gsf_host_free", "gsf_set_chunk_points", "gsf_set_variant", "gsf_set_profiling",
                  "gsf_get_last_stats", "gsf_dfma_peak", "gsf_abi_version", "gsf_device_count",
                  "gsf_shutdown"):
@@ -239,6 +260,103 @@ def summate_fourier(spectrum_factor, modes, z1, z2, pos, num_threads=None):
     if rc:
         _raise(rc)
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# extended calls: fused post-scale/offset and structured grids (8 f3)
+
+_KINDS = {"summate": 0, "summate_incompr": 1, "summate_fourier": 2}
+
+
+def _extended(kind, sf, cov_samples, z1, z2, pos, axes, scale, offset, num_threads):
+    L = _load()
+    cov, a1, a2 = _Arr(cov_samples, 2, "cov_samples"), _Arr(z1, 1, "z1"), _Arr(z2, 1, "z2")
+    d, n = cov.shape
+    if cov.shape[1] != a1.shape[0] or cov.shape[1] != a2.shape[0]:
+        raise ValueError("mode count mismatch")
+    r = GsfRequest()
+    r.struct_size = ctypes.sizeof(GsfRequest)
+    r.kind, r.dim, r.num_threads, r.n_modes = kind, d, _threads(num_threads), n
+    keep = [cov, a1, a2]
+    r.modes, r.modes_s0, r.modes_s1 = cov.ptr, cov.strides[0], cov.strides[1]
+    r.z1, r.z1_s, r.z2, r.z2_s = a1.ptr, a1.strides[0], a2.ptr, a2.strides[0]
+    if kind == 2:
+        s = _Arr(sf, 1, "spectrum_factor")
+        if s.shape[0] != n:
+            raise ValueError("spectrum_factor has %d entries, modes has %d" % (s.shape[0], n))
+        r.spectrum_factor, r.sf_s = s.ptr, s.strides[0]
+        keep.append(s)
+    if axes is not None:
+        axes = [np.ascontiguousarray(a, dtype=np.float64) for a in axes]
+        if len(axes) != d:
+            raise ValueError("need %d axis vectors, got %d" % (d, len(axes)))
+        if any(a.ndim != 1 for a in axes):
+            raise ValueError("axis vectors must be one-dimensional")
+        m = 1
+        for i, a in enumerate(axes):
+            r.axis[i], r.axis_n[i], r.axis_s[i] = a.ctypes.data, a.shape[0], 1
+            m *= a.shape[0]
+        r.n_axes = d
+        keep.append(axes)
+    else:
+        p = _Arr(pos, 2, "pos")
+        if p.shape[0] != d:
+            raise ValueError("dim mismatch: cov_samples has %d rows, pos has %d" % (d, p.shape[0]))
+        if p.device:
+            raise TypeError("pos is a device array; use the *_device functions")
+        m = p.shape[1]
+        r.pos, r.pos_s0, r.pos_s1 = p.ptr, p.strides[0], p.strides[1]
+        keep.append(p)
+    r.n_points = m
+    if kind == 1:
+        out = _result_array((d, m), order="F")
+        r.out_s0, r.out_s1 = out.strides[0] // 8, out.strides[1] // 8
+    else:
+        out = _result_array((m,))
+        r.out_s0, r.out_s1 = 0, 1
+    r.out = out.ctypes.data
+    r.scale = float(scale)
+    off = np.zeros(3)
+    off[:np.size(offset)] = np.ravel(offset)[:3]
+    for i in range(3):
+        r.offset[i] = float(off[i])
+    rc = L.gsf_summate_ex(ctypes.byref(r))
+    if rc:
+        _raise(rc)
+    return out
+
+
+def summate_scaled(cov_samples, z1, z2, pos, scale=1.0, offset=0.0, num_threads=None):
+    """scale * summate(...) + offset in one pass (GSTools: sqrt(var/N) * summed_modes + mean)."""
+    return _extended(0, None, cov_samples, z1, z2, pos, None, scale, offset, num_threads)
+
+
+def summate_incompr_scaled(cov_samples, z1, z2, pos, scale=1.0, offset=(0.0, 0.0, 0.0), num_threads=None):
+    """scale * summate_incompr(...) + offset[component] in one pass."""
+    return _extended(1, None, cov_samples, z1, z2, pos, None, scale, offset, num_threads)
+
+
+def summate_fourier_scaled(spectrum_factor, modes, z1, z2, pos, scale=1.0, offset=0.0, num_threads=None):
+    return _extended(2, spectrum_factor, modes, z1, z2, pos, None, scale, offset, num_threads)
+
+
+def summate_grid(cov_samples, z1, z2, axes, scale=1.0, offset=0.0, num_threads=None):
+    """summate on the rectilinear grid axes[0] x axes[1] (x axes[2]) (GSTools mesh_type="structured"):
+    same values as summate(..., pos=expanded grid flattened in C order), shape (prod(n_a),)."""
+    return _extended(0, None, cov_samples, z1, z2, None, axes, scale, offset, num_threads)
+
+
+def summate_incompr_grid(cov_samples, z1, z2, axes, scale=1.0, offset=(0.0, 0.0, 0.0), num_threads=None):
+    return _extended(1, None, cov_samples, z1, z2, None, axes, scale, offset, num_threads)
+
+
+def summate_fourier_grid(spectrum_factor, modes, z1, z2, axes, scale=1.0, offset=0.0, num_threads=None):
+    return _extended(2, spectrum_factor, modes, z1, z2, None, axes, scale, offset, num_threads)
+
+
+def set_grid_detection(enabled=True):
+    """Automatic structured-grid detection in summate*/(host pos): True/False, None = GSF_GRID_DETECT."""
+    _load().gsf_set_grid_detection(-1 if enabled is None else (1 if enabled else 0))
 
 
 # ---------------------------------------------------------------------------------------------

@@ -67,7 +67,7 @@ typedef struct gsf_stats {
     int32_t lanes_per_point;   /* L of the kernel variant used                                          */
     int32_t pos_memory;     /* 0 pageable host, 1 pinned host, 2 device                                  */
     int32_t out_memory;
-    int32_t reserved;
+    int32_t grid_path;      /* 0 general kernel, 1 structured grid auto-detected, 2 structured grid requested */
 } gsf_stats;
 
 /* ---- the three reference functions ------------------------------------------------------- */
@@ -97,6 +97,40 @@ int gsf_summate_fourier(int dim, int64_t n_modes, int64_t n_points,
                         const double *z2, int64_t z2_s,
                         const double *pos, int64_t pos_s0, int64_t pos_s1,
                         double *out, int num_threads);
+
+/* ---- extended request: fused post-scale / offset and structured grids ---------------------- */
+
+/* One struct for everything beyond the three reference signatures:
+ *   out[a, j] = scale * sum_i(...) + offset[a]      (GSTools applies sqrt(var/N) and the mean right
+ *                                                    after the call; here it costs nothing)
+ *   n_axes > 0: the points are the rectilinear grid axis[0] x axis[1] (x axis[2]) flattened in C
+ *   order (GSTools mesh_type="structured"); pos is ignored, n_points is prod(axis_n).  The sum then
+ *   factorises per axis and runs as an FP64 tensor-core GEMM (2 FMA per point*mode instead of 15).
+ * The plain entry points detect such grids in host-resident `pos` automatically (exact, bitwise
+ * check; gsf_set_grid_detection(0) or GSF_GRID_DETECT=0 turns that off).
+ * Set struct_size = sizeof(gsf_request); zero-initialise the rest you do not use (scale = 1). */
+typedef struct gsf_request {
+    int32_t struct_size;
+    int32_t kind;           /* 0 summate, 1 summate_incompr, 2 summate_fourier */
+    int32_t dim;
+    int32_t num_threads;
+    int64_t n_modes, n_points;
+    const double *spectrum_factor; int64_t sf_s;
+    const double *modes; int64_t modes_s0, modes_s1;
+    const double *z1; int64_t z1_s;
+    const double *z2; int64_t z2_s;
+    const double *pos; int64_t pos_s0, pos_s1;
+    double *out; int64_t out_s0, out_s1;
+    double scale;
+    double offset[3];
+    int32_t n_axes;         /* 0, or == dim (2 or 3) for a structured grid */
+    int32_t reserved;
+    const double *axis[3]; int64_t axis_n[3]; int64_t axis_s[3];   /* host-resident axis vectors */
+} gsf_request;
+
+int gsf_summate_ex(const gsf_request *request);
+/* 1 / 0: enable / disable automatic structured-grid detection; -1: follow GSF_GRID_DETECT (default on). */
+int gsf_set_grid_detection(int enabled);
 
 /* ---- stream-ordered variant for device-resident data -------------------------------------- */
 

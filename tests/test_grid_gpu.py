@@ -1,0 +1,169 @@
+"""GPU tests of the structured-grid path and the fused post-scale (8 f1).
+
+The grid path must return the same field as the general kernel / the CPU oracle on the expanded
+grid (tolerance 1e-9 sigma), both when requested explicitly with axis vectors and when the plain
+reference-shaped call detects the grid in `pos`.
+"""
+import numpy as np
+import pytest
+
+import gstools_core as gc
+import oracle
+from gstools_core import workloads
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+@pytest.fixture(autouse=True)
+def _reset():
+    if gc.device_count() < 1:
+        pytest.fail("no CUDA device")
+    gc.set_variant(0, 0)
+    gc.set_chunk_points(0)
+    gc.set_devices(None)
+    gc.set_grid_detection(None)
+    yield
+    gc.set_grid_detection(None)
+
+
+def rel_err(got, ref):
+    s = float(np.std(ref)) or 1.0
+    return float(np.max(np.abs(got - ref))) / s
+
+
+def expand(axes):
+    g = np.meshgrid(*axes, indexing="ij")
+    return np.ascontiguousarray(np.stack([x.ravel() for x in g]))
+
+
+def modes(seed, d, n, heavy=False):
+    rng = np.random.default_rng(seed)
+    k = rng.normal(size=(d, n))
+    if heavy:
+        k = k / np.abs(rng.normal(size=n))
+    return k, rng.normal(size=n), rng.normal(size=n), rng.normal(size=n)
+
+
+@pytest.mark.parametrize("shape", [(33, 20), (64, 100), (5, 7), (100, 8), (40, 300), (17, 1031)])
+@pytest.mark.parametrize("n", [1, 40, 257])
+def test_grid_2d_explicit(shape, n):
+    rng = np.random.default_rng(1)
+    axes = [np.sort(rng.uniform(-30, 30, s)) for s in shape]      # non-uniform rectilinear grid
+    k, z1, z2, sf = modes(2, 2, n)
+    pos = expand(axes)
+    ref = oracle.summate(k, z1, z2, pos, oracle.max_threads())
+    got = gc.summate_grid(k, z1, z2, axes)
+    assert gc.last_stats()["grid_path"] == 2
+    assert got.shape == ref.shape and rel_err(got, ref) <= TOL
+    reff = oracle.summate_fourier(sf, k, z1, z2, pos, oracle.max_threads())
+    assert rel_err(gc.summate_fourier_grid(sf, k, z1, z2, axes), reff) <= TOL
+    refi = oracle.summate_incompr(k, z1, z2, pos)
+    goti = gc.summate_incompr_grid(k, z1, z2, axes)
+    assert goti.shape == (2, pos.shape[1]) and goti.flags.f_contiguous
+    assert rel_err(goti, refi) <= TOL
+
+
+@pytest.mark.parametrize("shape", [(10, 11, 12), (3, 50, 100), (32, 1, 64), (1, 40, 40), (21, 22, 130), (9, 9, 700)])
+@pytest.mark.parametrize("n", [33, 1000])
+def test_grid_3d_explicit(shape, n):
+    rng = np.random.default_rng(3)
+    axes = [np.sort(rng.uniform(0, 100, s)) for s in shape]
+    k, z1, z2, sf = modes(4, 3, n, heavy=True)
+    pos = expand(axes)
+    ref = oracle.summate(k, z1, z2, pos, oracle.max_threads())
+    got = gc.summate_grid(k, z1, z2, axes)
+    assert rel_err(got, ref) <= TOL
+    refi = oracle.summate_incompr(k, z1, z2, pos, 1)
+    assert rel_err(gc.summate_incompr_grid(k, z1, z2, axes), refi) <= TOL
+
+
+def test_auto_detection_matches_general_kernel():
+    axes = [np.linspace(0, 50, 41), np.linspace(-5, 5, 37), np.linspace(2, 9, 64)]
+    pos = expand(axes)
+    k, z1, z2, sf = modes(5, 3, 300, heavy=True)
+    gc.set_grid_detection(False)
+    gen = gc.summate(k, z1, z2, pos)
+    assert gc.last_stats()["grid_path"] == 0
+    gc.set_grid_detection(True)
+    auto = gc.summate(k, z1, z2, pos)
+    assert gc.last_stats()["grid_path"] == 1
+    assert rel_err(auto, gen) <= TOL
+    assert rel_err(auto, oracle.summate(k, z1, z2, pos, oracle.max_threads())) <= TOL
+    # incompr + fourier through the reference-shaped calls
+    assert rel_err(gc.summate_incompr(k, z1, z2, pos), oracle.summate_incompr(k, z1, z2, pos)) <= TOL
+    assert gc.last_stats()["grid_path"] == 1
+    assert rel_err(gc.summate_fourier(sf, k, z1, z2, pos), oracle.summate_fourier(sf, k, z1, z2, pos)) <= TOL
+
+
+def test_detection_rejects_non_grids():
+    axes = [np.linspace(0, 50, 41), np.linspace(-5, 5, 37), np.linspace(2, 9, 64)]
+    pos = expand(axes)
+    k, z1, z2, _ = modes(6, 3, 64)
+    gc.set_grid_detection(True)
+    for mutate in (lambda p: p.__setitem__((2, 12345), p[2, 12345] + 1e-13),     # one perturbed point
+                   lambda p: p.__setitem__((0, -1), np.nextafter(p[0, -1], 1e9)),
+                   lambda p: p.__setitem__((1, 64 * 5 + 3), -p[1, 64 * 5 + 3] - 1.0)):
+        q = pos.copy()
+        mutate(q)
+        got = gc.summate(k, z1, z2, q)
+        assert gc.last_stats()["grid_path"] == 0                   # exact check failed -> general kernel
+        assert rel_err(got, oracle.summate(k, z1, z2, q, oracle.max_threads())) <= TOL
+    # random points, a line (C1-like), F-ordered meshgrid (xy indexing) are not C-order grids
+    rng = np.random.default_rng(0)
+    rnd = rng.uniform(0, 10, size=(3, 70000))
+    gc.summate(k, z1, z2, rnd)
+    assert gc.last_stats()["grid_path"] == 0
+    line = np.stack([np.linspace(0, 10, 50000)] * 3)
+    gc.summate(k, z1, z2, line)
+    assert gc.last_stats()["grid_path"] == 0
+    gx = np.meshgrid(*axes, indexing="xy")
+    posxy = np.ascontiguousarray(np.stack([g.ravel() for g in gx]))
+    got = gc.summate(k, z1, z2, posxy)
+    assert rel_err(got, oracle.summate(k, z1, z2, posxy, oracle.max_threads())) <= TOL
+
+
+def test_scale_and_offset_fusion():
+    k, z1, z2, sf = modes(7, 3, 200)
+    rng = np.random.default_rng(1)
+    pos = rng.uniform(0, 20, size=(3, 5000))
+    base = gc.summate(k, z1, z2, pos)
+    got = gc.summate_scaled(k, z1, z2, pos, scale=0.37, offset=2.5)
+    assert np.max(np.abs(got - (0.37 * base + 2.5))) <= 1e-12 * max(1.0, np.std(base))
+    basei = gc.summate_incompr(k, z1, z2, pos)
+    goti = gc.summate_incompr_scaled(k, z1, z2, pos, scale=1.5, offset=(3.0, 0.0, -1.0))
+    want = 1.5 * basei + np.array([[3.0], [0.0], [-1.0]])
+    assert np.max(np.abs(goti - want)) <= 1e-12 * max(1.0, np.std(basei))
+    axes = [np.linspace(0, 9, 30), np.linspace(0, 5, 20), np.linspace(0, 1, 16)]
+    g0 = gc.summate_grid(k, z1, z2, axes)
+    g1 = gc.summate_grid(k, z1, z2, axes, scale=2.0, offset=-0.5)
+    assert np.max(np.abs(g1 - (2.0 * g0 - 0.5))) <= 1e-12 * max(1.0, np.std(g0))
+    # every lanes-per-point variant adds the offset exactly once
+    for P, L in [(1, 4), (2, 8), (1, 32)]:
+        gc.set_variant(P, L)
+        v = gc.summate_scaled(k, z1, z2, pos, scale=0.37, offset=2.5)
+        assert np.max(np.abs(v - (0.37 * base + 2.5))) <= 1e-11 * max(1.0, np.std(base))
+
+
+@pytest.mark.parametrize("cfg", ["c2", "c3", "c4", "c5"])
+def test_baseline_configs_grid_vs_general(cfg):
+    """Full-size BASELINE grids: auto-detected grid path vs the oracle on a strided subset (and vs
+    the general kernel for the configs where that takes well under a second)."""
+    w = workloads.make(cfg)
+    fn = getattr(gc, w["kind"])
+    gc.set_grid_detection(True)
+    got = fn(*w["args"])
+    st = gc.last_stats()
+    assert st["grid_path"] == 1
+    m = w["m"]
+    idx = np.unique(np.concatenate([np.arange(0, m, max(1, m // 6000)), np.arange(2048), np.arange(m - 2048, m)]))
+    ref = getattr(oracle, w["kind"])(*workloads.subset_points(w, idx)["args"], oracle.max_threads())
+    sub = got[:, idx] if got.ndim == 2 else got[idx]
+    e = rel_err(sub, ref)
+    print("%s grid path: max|d|/sigma=%.3g total_ms=%.2f chunks=%d" % (cfg, e, st["total_ms"], st["n_chunks"]))
+    assert e <= TOL
+    if cfg in ("c2", "c3"):
+        gc.set_grid_detection(False)
+        gen = fn(*w["args"])
+        assert gc.last_stats()["grid_path"] == 0
+        assert rel_err(got, gen) <= TOL
