@@ -299,6 +299,28 @@ __global__ void __launch_bounds__(kGridThreads) gsf_grid_gemm(GridGemmArgs a)
 }
 
 // ------------------------------------------------------------------------------------------
+// FP64 tensor-path peak: independent DMMA.8x8x4 accumulator chains, all SMs, full occupancy.
+// The roofline denominator of gsf_grid_gemm (256 FMA per warp-level DMMA).
+constexpr int kDmmaChains = 2;
+constexpr int kDmmaUnroll = 32;
+__global__ void __launch_bounds__(256) gsf_dmma_peak_kernel(double *sink, int iters, double a, double b)
+{
+    double c0[kDmmaChains], c1[kDmmaChains];
+#pragma unroll
+    for (int i = 0; i < kDmmaChains; ++i) { c0[i] = i; c1[i] = -i; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < kDmmaUnroll; ++u)
+#pragma unroll
+            for (int i = 0; i < kDmmaChains; ++i) dmma884(c0[i], c1[i], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < kDmmaChains; ++i) s += c0[i] + c1[i];
+    if (s == 123.456) sink[0] = s;
+}
+
+// ------------------------------------------------------------------------------------------
 // Exact test "is pos a C-order flattened rectilinear grid?" for device-resident positions:
 // every point must equal (axis0[j0], axis1[j1], axis2[j2]) bit for bit, where the candidate axes
 // are read from pos itself (first occurrence along each axis).  flag[0] is set to 1 on mismatch.

@@ -1230,7 +1230,7 @@ int gsf_shutdown(void)
     return GSF_OK;
 }
 
-int gsf_dfma_peak(int device, double min_ms, double *dfma_per_s, double *elapsed_ms)
+static int fp64_peak(int device, double min_ms, bool tensor, double *per_s, double *elapsed_ms)
 {
     Context &c = ctx();
     std::lock_guard<std::mutex> lock(c.mu);
@@ -1247,11 +1247,14 @@ int gsf_dfma_peak(int device, double min_ms, double *dfma_per_s, double *elapsed
     const int threads = 256;
     const int blocks = d->sm_count * 8;   // 2048 threads per SM
     cudaStream_t st = d->slot[0].stream;
-    int iters = 2000;
+    int iters = tensor ? 200 : 2000;
     float ms = 0.f;
-    for (int attempt = 0; attempt < 12; ++attempt) {
+    for (int attempt = 0; attempt < 14; ++attempt) {
         GSF_CUDA(cudaEventRecord(e0, st));
-        gsf::gsf_dfma_peak_kernel<<<blocks, threads, 0, st>>>(sink, iters, 0.999999, 1e-9);
+        if (tensor)
+            gsf::gsf_dmma_peak_kernel<<<blocks, threads, 0, st>>>(sink, iters, 0.999999, 1e-9);
+        else
+            gsf::gsf_dfma_peak_kernel<<<blocks, threads, 0, st>>>(sink, iters, 0.999999, 1e-9);
         GSF_CUDA(cudaGetLastError());
         GSF_CUDA(cudaEventRecord(e1, st));
         GSF_CUDA(cudaEventSynchronize(e1));
@@ -1260,13 +1263,27 @@ int gsf_dfma_peak(int device, double min_ms, double *dfma_per_s, double *elapsed
         const double scale = ms > 0.05 ? std::min(16.0, 1.25 * min_ms / ms) : 16.0;
         iters = (int)std::min<double>((double)iters * std::max(scale, 1.5), 1 << 29);
     }
-    const double n = (double)blocks * threads * (double)iters * gsf::kPeakChains * gsf::kPeakUnroll;
-    if (dfma_per_s) *dfma_per_s = n / (ms * 1e-3);
+    double n;
+    if (tensor)   // thread-level FMA: 256 per warp-level DMMA
+        n = (double)blocks * (threads / 32) * (double)iters * gsf::kDmmaChains * gsf::kDmmaUnroll * 256.0;
+    else
+        n = (double)blocks * threads * (double)iters * gsf::kPeakChains * gsf::kPeakUnroll;
+    if (per_s) *per_s = n / (ms * 1e-3);
     if (elapsed_ms) *elapsed_ms = ms;
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     cudaFree(sink);
     return GSF_OK;
+}
+
+int gsf_dfma_peak(int device, double min_ms, double *dfma_per_s, double *elapsed_ms)
+{
+    return fp64_peak(device, min_ms, false, dfma_per_s, elapsed_ms);
+}
+
+int gsf_dmma_peak(int device, double min_ms, double *fma_per_s, double *elapsed_ms)
+{
+    return fp64_peak(device, min_ms, true, fma_per_s, elapsed_ms);
 }
 
 }  // extern "C"

@@ -99,6 +99,8 @@ def _load():
     L.gsf_get_last_stats.argtypes = [ctypes.POINTER(GsfStats)]
     L.gsf_dfma_peak.argtypes = [_int, ctypes.c_double, ctypes.POINTER(ctypes.c_double),
                                 ctypes.POINTER(ctypes.c_double)]
+    L.gsf_dmma_peak.argtypes = L.gsf_dfma_peak.argtypes
+    L.gsf_dmma_peak.restype = _int
     L.gsf_last_error.restype = ctypes.c_char_p
     for name in ("gsf_summate", "gsf_summate_incompr", "gsf_summate_fourier", "gsf_summate_on_stream",
                  "gsf_summate_ex", "gsf_set_grid_detection",
@@ -268,7 +270,7 @@ def summate_fourier(spectrum_factor, modes, z1, z2, pos, num_threads=None):
 _KINDS = {"summate": 0, "summate_incompr": 1, "summate_fourier": 2}
 
 
-def _extended(kind, sf, cov_samples, z1, z2, pos, axes, scale, offset, num_threads):
+def _extended(kind, sf, cov_samples, z1, z2, pos, axes, scale, offset, num_threads, out=None):
     L = _load()
     cov, a1, a2 = _Arr(cov_samples, 2, "cov_samples"), _Arr(z1, 1, "z1"), _Arr(z2, 1, "z2")
     d, n = cov.shape
@@ -308,13 +310,25 @@ def _extended(kind, sf, cov_samples, z1, z2, pos, axes, scale, offset, num_threa
         r.pos, r.pos_s0, r.pos_s1 = p.ptr, p.strides[0], p.strides[1]
         keep.append(p)
     r.n_points = m
-    if kind == 1:
+    if out is not None:
+        # caller-provided result (host ndarray or device array), e.g. to keep the field on the GPU
+        o = _Arr(out, 2 if kind == 1 else 1, "out")
+        if o.shape != ((d, m) if kind == 1 else (m,)):
+            raise ValueError("out has shape %s, expected %s" % (o.shape, (d, m) if kind == 1 else (m,)))
+        if kind == 1:
+            r.out_s0, r.out_s1 = o.strides
+        else:
+            r.out_s0, r.out_s1 = 0, o.strides[0] if m > 1 else 1
+        r.out = o.ptr
+        keep.append(o)
+    elif kind == 1:
         out = _result_array((d, m), order="F")
         r.out_s0, r.out_s1 = out.strides[0] // 8, out.strides[1] // 8
+        r.out = out.ctypes.data
     else:
         out = _result_array((m,))
         r.out_s0, r.out_s1 = 0, 1
-    r.out = out.ctypes.data
+        r.out = out.ctypes.data
     r.scale = float(scale)
     off = np.zeros(3)
     off[:np.size(offset)] = np.ravel(offset)[:3]
@@ -340,18 +354,18 @@ def summate_fourier_scaled(spectrum_factor, modes, z1, z2, pos, scale=1.0, offse
     return _extended(2, spectrum_factor, modes, z1, z2, pos, None, scale, offset, num_threads)
 
 
-def summate_grid(cov_samples, z1, z2, axes, scale=1.0, offset=0.0, num_threads=None):
+def summate_grid(cov_samples, z1, z2, axes, scale=1.0, offset=0.0, num_threads=None, out=None):
     """summate on the rectilinear grid axes[0] x axes[1] (x axes[2]) (GSTools mesh_type="structured"):
     same values as summate(..., pos=expanded grid flattened in C order), shape (prod(n_a),)."""
-    return _extended(0, None, cov_samples, z1, z2, None, axes, scale, offset, num_threads)
+    return _extended(0, None, cov_samples, z1, z2, None, axes, scale, offset, num_threads, out)
 
 
-def summate_incompr_grid(cov_samples, z1, z2, axes, scale=1.0, offset=(0.0, 0.0, 0.0), num_threads=None):
-    return _extended(1, None, cov_samples, z1, z2, None, axes, scale, offset, num_threads)
+def summate_incompr_grid(cov_samples, z1, z2, axes, scale=1.0, offset=(0.0, 0.0, 0.0), num_threads=None, out=None):
+    return _extended(1, None, cov_samples, z1, z2, None, axes, scale, offset, num_threads, out)
 
 
-def summate_fourier_grid(spectrum_factor, modes, z1, z2, axes, scale=1.0, offset=0.0, num_threads=None):
-    return _extended(2, spectrum_factor, modes, z1, z2, None, axes, scale, offset, num_threads)
+def summate_fourier_grid(spectrum_factor, modes, z1, z2, axes, scale=1.0, offset=0.0, num_threads=None, out=None):
+    return _extended(2, spectrum_factor, modes, z1, z2, None, axes, scale, offset, num_threads, out)
 
 
 def set_grid_detection(enabled=True):
@@ -461,6 +475,15 @@ def dfma_peak(device=0, min_ms=200.0):
     """Measured FP64 DFMA rate of `device` in thread-level DFMA/s (the roofline denominator)."""
     rate, ms = ctypes.c_double(), ctypes.c_double()
     rc = _load().gsf_dfma_peak(int(device), float(min_ms), ctypes.byref(rate), ctypes.byref(ms))
+    if rc:
+        _raise(rc)
+    return rate.value, ms.value
+
+
+def dmma_peak(device=0, min_ms=200.0):
+    """Measured FP64 tensor-path (DMMA) rate in thread-level FMA/s: roofline of the grid kernel."""
+    rate, ms = ctypes.c_double(), ctypes.c_double()
+    rc = _load().gsf_dmma_peak(int(device), float(min_ms), ctypes.byref(rate), ctypes.byref(ms))
     if rc:
         _raise(rc)
     return rate.value, ms.value

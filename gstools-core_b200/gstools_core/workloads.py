@@ -35,6 +35,11 @@ def _grid(shape, spacing, out=None):
     return pos
 
 
+def _axes(shape, spacing):
+    """The axis vectors whose C-order expansion `_grid` returns (bit-identical values)."""
+    return [np.arange(n, dtype=np.float64) * h for n, h in zip(shape, spacing)]
+
+
 def gaussian_modes(rng, d, n, len_scale):
     # GSTools Gaussian model with rescale sqrt(pi)/2: k ~ N(0, (pi/2)/l^2 I)
     return rng.normal(size=(d, n)) * np.sqrt(np.pi / 2.0) / len_scale
@@ -58,7 +63,7 @@ def make(config, scale=1.0, pos_out=None):
         k = gaussian_modes(rng, 2, n, 1.0)
         z1, z2 = rng.normal(size=n), rng.normal(size=n)
         pos = np.stack([np.linspace(0.0, 10.0, m), np.linspace(-5.0, 5.0, m)])
-        return dict(kind="summate", args=(k, z1, z2, pos), d=2, n=n, m=m)
+        return dict(kind="summate", args=(k, z1, z2, pos), d=2, n=n, m=m, axes=None)
     if c in ("c2", "c5"):
         rng = np.random.default_rng(2 if c == "c2" else 5)
         n = 1000 if c == "c2" else 10_000
@@ -72,7 +77,7 @@ def make(config, scale=1.0, pos_out=None):
             shape = (max(2, int(round(1000 * f))), max(2, int(round(1000 * f))), max(2, int(round(100 * f))))
             spacing = (0.1, 0.1, 0.1)
         pos = _grid(shape, spacing, pos_out)
-        return dict(kind="summate", args=(k, z1, z2, pos), d=3, n=n, m=pos.shape[1])
+        return dict(kind="summate", args=(k, z1, z2, pos), d=3, n=n, m=pos.shape[1], axes=_axes(shape, spacing))
     if c == "c3":
         rng = np.random.default_rng(3)
         n = 1000
@@ -80,7 +85,8 @@ def make(config, scale=1.0, pos_out=None):
         z1, z2 = rng.normal(size=n), rng.normal(size=n)
         side = max(2, int(round(100 * scale ** (1 / 3))))
         pos = _grid((side, side, side), (1.0, 1.0, 1.0), pos_out)
-        return dict(kind="summate_incompr", args=(k, z1, z2, pos), d=3, n=n, m=pos.shape[1])
+        return dict(kind="summate_incompr", args=(k, z1, z2, pos), d=3, n=n, m=pos.shape[1],
+                    axes=_axes((side, side, side), (1.0, 1.0, 1.0)))
     if c == "c4":
         rng = np.random.default_rng(4)
         period, ell, nm = 100.0, 5.0, 100
@@ -94,7 +100,8 @@ def make(config, scale=1.0, pos_out=None):
         z1, z2 = rng.normal(size=n), rng.normal(size=n)
         side = max(2, int(round(4096 * scale ** 0.5)))
         pos = _grid((side, side), (period / side, period / side), pos_out)
-        return dict(kind="summate_fourier", args=(sf, modes, z1, z2, pos), d=2, n=n, m=pos.shape[1])
+        return dict(kind="summate_fourier", args=(sf, modes, z1, z2, pos), d=2, n=n, m=pos.shape[1],
+                    axes=_axes((side, side), (period / side, period / side)))
     raise ValueError("unknown config %r" % config)
 
 
@@ -102,4 +109,4 @@ def subset_points(w, idx):
     """Same workload restricted to the point columns `idx` (for oracle checks of big configs)."""
     args = list(w["args"])
     args[-1] = np.ascontiguousarray(args[-1][:, idx])
-    return dict(w, args=tuple(args), m=len(idx))
+    return dict(w, args=tuple(args), m=len(idx), axes=None)

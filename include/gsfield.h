@@ -179,6 +179,9 @@ int gsf_shutdown(void);
  * measured with CUDA events over ~`min_ms` milliseconds of dependent-chain DFMAs at full
  * occupancy.  This is the measured roofline denominator. */
 int gsf_dfma_peak(int device, double min_ms, double *dfma_per_s, double *elapsed_ms);
+/* Same for the FP64 tensor path (DMMA.8x8x4 streams), in thread-level FMA per second: the
+ * roofline denominator of the structured-grid GEMM kernel. */
+int gsf_dmma_peak(int device, double min_ms, double *fma_per_s, double *elapsed_ms);
 
 #ifdef __cplusplus
 }
