@@ -33,9 +33,11 @@ constexpr int kGridRows = 32;       // rows per CTA (8 per warp)
 constexpr int kGridBK = 16;         // modes per K block (32 contraction steps)
 constexpr int kGridMaxNT = 16;      // column tiles (of 8) per CTA
 constexpr int kGStride = 2 * kGridBK + 4;   // doubles per G row in smem (36: conflict-free LDS.64)
-// doubles per F row in smem/global tiles: 8*NT padded so that it is 8 mod 16 -- the four k-rows
-// of a DMMA B fragment then fall into complementary bank halves (2 wavefronts, the minimum).
-__host__ __device__ constexpr int grid_bnp(int nt) { return 8 * nt + ((nt & 1) ? 0 : 8); }
+// doubles per F row in smem/global tiles: 8*NT + 4, i.e. 4 or 12 mod 16.  A 64-bit shared load is
+// served per half-warp; the 16 lanes of a DMMA B fragment half read 4 k-rows x 4 columns, and
+// with this stride the four rows start 8 banks apart (0/8/16/24): one wavefront per half-warp.
+// (8 mod 16 puts rows 0/2 and 1/3 on the same banks: measured 2x the wavefronts, smem-bound.)
+__host__ __device__ constexpr int grid_bnp(int nt) { return 8 * nt + 4; }
 __host__ __device__ constexpr size_t grid_smem_bytes(int nt)
 {
     return (size_t)(2 * (2 * kGridBK * grid_bnp(nt)) + 2 * (kGridRows * kGStride)) * sizeof(double) + 16;
@@ -46,7 +48,7 @@ __host__ __device__ constexpr size_t grid_smem_bytes(int nt)
 //   E tables (axes 0 .. D-2): layout [n_a][Npad] complex (re, im), modes fastest.
 //   F table (last axis): tiled for the GEMM kernel,
 //       F[colblock][kappa = 2*i + {0: re, 1: -im}][BNp]  with column = j*NC + comp inside a block;
-//     BNp = 8*NT + 8 padding doubles (zero) so the smem image is bank-conflict free as copied.
+//     BNp = 8*NT + 4 doubles (padding zero) so the smem image is bank-conflict free as copied.
 struct GridTableArgs {
     const double *rec; int rec_doubles; int dim; int nc;
     int64_t n_modes, n_modes_pad;

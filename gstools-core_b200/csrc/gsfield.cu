@@ -1254,7 +1254,7 @@ static int fp64_peak(int device, double min_ms, bool tensor, double *per_s, doub
         if (tensor)
             gsf::gsf_dmma_peak_kernel<<<blocks, threads, 0, st>>>(sink, iters, 0.999999, 1e-9);
         else
-            gsf::gsf_dfma_peak_kernel<<<blocks, threads, 0, st>>>(sink, iters, 0.999999, 1e-9);
+            gsf::gsf_dfma_peak_kernel<<<blocks, threads, 0, st>>>(sink, iters, -1e-12, 1e-9);
         GSF_CUDA(cudaGetLastError());
         GSF_CUDA(cudaEventRecord(e1, st));
         GSF_CUDA(cudaEventSynchronize(e1));
