@@ -213,13 +213,24 @@ __global__ void __launch_bounds__(kGridThreads) gsf_grid_gemm(GridGemmArgs a)
 #pragma unroll
     for (int t = 0; t < NT; ++t) acc[t][0] = acc[t][1] = 0.0;
 
-    if (kb0 < kb1) load_e(kb0);
+    // Software pipeline, ONE __syncthreads per K block:
+    //   iteration kb reads stage st = (kb-kb0)&1 (F landed by TMA two blocks ago, G written one
+    //   block ago), writes G(kb+1) into the other stage from registers prefetched one block ago,
+    //   and issues the E loads for kb+2.  The trailing barrier both publishes G(kb+1) and
+    //   releases stage st for the TMA refill / the G(kb+2) stores.
+    if (kb0 < kb1) {
+        load_e(kb0);
+        store_g(0);
+        if (kb0 + 1 < kb1) load_e(kb0 + 1);
+    }
+    __syncthreads();
     for (int64_t kb = kb0; kb < kb1; ++kb) {
         const int st = (int)((kb - kb0) & 1);
-        store_g(st);                                   // G(kb) from the registers loaded earlier
-        if (kb + 1 < kb1) load_e(kb + 1);              // prefetch E for the next block
+        if (kb + 1 < kb1) {
+            store_g(st ^ 1);                           // G(kb+1)
+            if (kb + 2 < kb1) load_e(kb + 2);          // prefetch E for kb+2
+        }
         mbar_wait(&bar[st], (uint32_t)(((kb - kb0) >> 1) & 1));
-        __syncthreads();                               // G(kb) visible, F(kb) landed
 
         const double *g = sG + st * GSTAGE + (warp * 8 + (lane >> 2)) * kGStride + (lane & 3);
         const double *f = sF + st * FSTAGE + (lane & 3) * BNP + (lane >> 2);
@@ -229,7 +240,7 @@ __global__ void __launch_bounds__(kGridThreads) gsf_grid_gemm(GridGemmArgs a)
 #pragma unroll
             for (int t = 0; t < NT; ++t) dmma884(acc[t][0], acc[t][1], af, f[(4 * k4) * BNP + 8 * t]);
         }
-        __syncthreads();                               // everyone done with stage st
+        __syncthreads();
         if (tid == 0 && kb + 2 < kb1) issue_f(kb + 2);
     }
 

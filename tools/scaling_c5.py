@@ -17,6 +17,9 @@ ndev = gc.device_count()
 print("devices", ndev, "workload", cfg, "points", w["m"], "modes", w["n"], flush=True)
 t0 = time.perf_counter(); pinned = torch.from_numpy(args[-1]).pin_memory().numpy(); print("pin_memory %.2f s" % (time.perf_counter() - t0), flush=True)
 res = {}
+mode = sys.argv[3] if len(sys.argv) > 3 else "general"
+gc.set_grid_detection(mode == "grid")
+print("path:", mode, flush=True)
 for label, pos in (("pinned", pinned), ("pageable", args[-1])):
     base = None
     for g in [1, 2, 4, 8]:
@@ -31,8 +34,8 @@ for label, pos in (("pinned", pinned), ("pageable", args[-1])):
         if base is None: base = (t, out.copy())
         same = bool(np.array_equal(out, base[1]))
         st = gc.last_stats()
-        print("%s G=%d: %.1f ms  %.0f Gpm/s  speedup %.2fx  devices_used=%d chunks=%d identical_to_G1=%s"
-              % (label, g, t * 1e3, pm / t / 1e9, base[0] / t, st["n_devices"], st["n_chunks"], same), flush=True)
+        print("%s G=%d: %.1f ms  %.0f Gpm/s  speedup %.2fx  devices_used=%d chunks=%d grid_path=%d identical_to_G1=%s"
+              % (label, g, t * 1e3, pm / t / 1e9, base[0] / t, st["n_devices"], st["n_chunks"], st["grid_path"], same), flush=True)
         res["%s_G%d" % (label, g)] = {"ms": t * 1e3, "gpm_s": pm / t / 1e9, "speedup": base[0] / t}
         del out
 print(json.dumps(res))
