@@ -191,23 +191,40 @@ struct SumArgs {
     double *out;                  // out[a*os0 + j*os1]
     int64_t os0, os1;
     double offset[3];             // added once per output component (fused post-offset)
+    int64_t n_big;                // number of leading tiles with P points per thread (rest: 1 point)
+    double coef[8];               // GSF_U0..U6: kernel parameters live in constant bank 0, which
+                                  // DFMA reads as a direct operand (no register, no RF read port)
 };
 
 // D: spatial dimension; NC: accumulators per point (1 scalar/fourier, D incompr);
 // P: points per thread; L: lanes sharing one point (modes split over them).
+// Source-level schedule knobs, chosen per (D, NC, P) by measurement on B200
+// (tools/micro/tune_sum.cu): ptxas' instruction order decides how often the operand-reuse cache
+// hits, and that is worth several percent on an FP64-bound loop.
+//   style 0: one point after the other; style 1: all P points in lockstep, step by step.
+#ifndef GSF_TUNE_STYLE
+template <int D, int NC, int P>
+__host__ __device__ constexpr int gsf_style() { return 1; }
+template <int D, int NC, int P>
+__host__ __device__ constexpr int gsf_unroll() { return (D == 3 && NC == 1 && P == 3) ? 4 : 8; }
+#else
+template <int D, int NC, int P>
+__host__ __device__ constexpr int gsf_style() { return GSF_TUNE_STYLE; }
+template <int D, int NC, int P>
+__host__ __device__ constexpr int gsf_unroll() { return GSF_TUNE_UNROLL; }
+#endif
+
+// Body for one CTA tile starting at point tile0 (P points per thread).
 template <int D, int NC, int P, int L>
-__global__ void __launch_bounds__(kThreads) gsf_sum_kernel(SumArgs a)
+__device__ __forceinline__ void sum_tile(const SumArgs &a, const int64_t tile0,
+                                         double (*s_rec)[kModeBlock * rec_doubles(D, NC)], uint64_t *s_bar)
 {
     constexpr int R = rec_doubles(D, NC);
     constexpr int kGroups = kThreads / L;            // point slots per CTA pass
-    constexpr int kTile = kGroups * P;               // points per CTA
-    __shared__ __align__(128) double s_rec[kStages][kModeBlock * R];
-    __shared__ __align__(8) uint64_t s_bar[kStages];
 
     const int tid = threadIdx.x;
     const int sub = tid % L;                         // which slice of the modes
     const int grp = tid / L;                         // which point slot
-    const int64_t tile0 = (int64_t)blockIdx.x * kTile;
 
     // ---- positions -> registers (coalesced: consecutive groups read consecutive points)
     double x[P][D];
@@ -227,7 +244,7 @@ __global__ void __launch_bounds__(kThreads) gsf_sum_kernel(SumArgs a)
 #pragma unroll
         for (int c = 0; c < NC; ++c) acc[p][c] = sub == 0 ? a.offset[c < 3 ? c : 0] : 0.0;
 
-    const PolyCoef coef = load_coef();
+    const PolyCoef coef = {a.coef[0], a.coef[1], a.coef[2], a.coef[3], a.coef[4], a.coef[5], a.coef[6]};
 
     // ---- mode ring: thread 0 is the producer
     const int64_t n_blocks = (a.n_modes + kModeBlock - 1) / kModeBlock;
@@ -257,7 +274,7 @@ __global__ void __launch_bounds__(kThreads) gsf_sum_kernel(SumArgs a)
         const int cnt = (int)((a.n_modes - m0) < kModeBlock ? (a.n_modes - m0) : kModeBlock);
         const double *blk = &s_rec[st][0];
 
-        constexpr int kUnroll = P >= 4 ? 2 : (P >= 2 ? 4 : 8);
+        constexpr int kUnroll = gsf_unroll<D, NC, P>();
 #pragma unroll kUnroll
         for (int i = sub; i < cnt; i += L) {
             const double *m = blk + i * R;
@@ -267,14 +284,60 @@ __global__ void __launch_bounds__(kThreads) gsf_sum_kernel(SumArgs a)
             nth = m[D];
 #pragma unroll
             for (int c = 0; c < NC; ++c) amp[c] = m[D + 1 + c];
+            if (gsf_style<D, NC, P>() == 0) {
+                // one point after the other (ptxas interleaves the chains itself)
+#pragma unroll
+                for (int p = 0; p < P; ++p) {
+                    double t = nth;
+#pragma unroll
+                    for (int d = 0; d < D; ++d) t = fma(kh[d], x[p][d], t);
+                    const double y = cospi_signed(t, coef);
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) acc[p][c] = fma(amp[c], y, acc[p][c]);
+                }
+            } else {
+            // The P points advance in lockstep, one step of the recipe at a time: consecutive
+            // instructions then share the mode operand (kh[d], a coefficient, amp[c]) in the same
+            // source slot, which ptxas serves from the operand-reuse cache -- a DFMA with three
+            // fresh register sources costs 3 cycles instead of 2 on B200.
+            double t[P], tn[P], sq[P], u[P];
+#pragma unroll
+            for (int p = 0; p < P; ++p) t[p] = fma(kh[0], x[p][0], nth);
+#pragma unroll
+            for (int d = 1; d < D; ++d)
+#pragma unroll
+                for (int p = 0; p < P; ++p) t[p] = fma(kh[d], x[p][d], t[p]);
+#pragma unroll
+            for (int p = 0; p < P; ++p) tn[p] = __dadd_rn(t[p], kMagic);       // low bits = rint(t)
 #pragma unroll
             for (int p = 0; p < P; ++p) {
-                double t = nth;
+                const double nf = __dadd_rn(tn[p], -kMagic);
+                const double r = __dadd_rn(t[p], -nf);                          // exact, |r| <= 1/2
+                sq[p] = __dmul_rn(r, r);
+            }
 #pragma unroll
-                for (int d = 0; d < D; ++d) t = fma(kh[d], x[p][d], t);
-                const double y = cospi_signed(t, coef);
+            for (int p = 0; p < P; ++p) u[p] = fma(coef.c6, sq[p], coef.c5);
 #pragma unroll
-                for (int c = 0; c < NC; ++c) acc[p][c] = fma(amp[c], y, acc[p][c]);
+            for (int p = 0; p < P; ++p) u[p] = fma(u[p], sq[p], coef.c4);
+#pragma unroll
+            for (int p = 0; p < P; ++p) u[p] = fma(u[p], sq[p], coef.c3);
+#pragma unroll
+            for (int p = 0; p < P; ++p) u[p] = fma(u[p], sq[p], coef.c2);
+#pragma unroll
+            for (int p = 0; p < P; ++p) u[p] = fma(u[p], sq[p], coef.c1);
+#pragma unroll
+            for (int p = 0; p < P; ++p) u[p] = fma(u[p], sq[p], coef.c0);
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                const double y = fma(u[p], u[p], -1.0);                         // cos(pi r)
+                const uint32_t hi = static_cast<uint32_t>(__double2hiint(y)) +
+                                    (static_cast<uint32_t>(__double2loint(tn[p])) << 31);
+                u[p] = __hiloint2double(static_cast<int>(hi), __double2loint(y));   // (-1)^n cos(pi r)
+            }
+#pragma unroll
+            for (int c = 0; c < NC; ++c)
+#pragma unroll
+                for (int p = 0; p < P; ++p) acc[p][c] = fma(amp[c], u[p], acc[p][c]);
             }
         }
         __syncthreads();                              // everyone is done with stage st
@@ -296,6 +359,29 @@ __global__ void __launch_bounds__(kThreads) gsf_sum_kernel(SumArgs a)
             for (int c = 0; c < NC; ++c) a.out[c * a.os0 + jpt[p] * a.os1] = acc[p][c];
         }
     }
+}
+
+// The kernel.  Tiles [0, n_big) carry P points per thread; the remaining tiles carry ONE point per
+// thread (a third of the work for P = 3).  The block scheduler hands out CTAs in index order, so
+// the short tiles run last: the machine drains in steps of the short tile, which removes most of
+// the end-of-kernel imbalance (17 vs 18 long CTAs per SM at C2) and partial-occupancy tail.
+template <int D, int NC, int P, int L>
+__global__ void __launch_bounds__(kThreads) gsf_sum_kernel(SumArgs a)
+{
+    constexpr int R = rec_doubles(D, NC);
+    __shared__ __align__(128) double s_rec[kStages][kModeBlock * R];
+    __shared__ __align__(8) uint64_t s_bar[kStages];
+    constexpr int kTile = (kThreads / L) * P;        // points per long tile
+    const int64_t b = blockIdx.x;
+#ifdef GSF_NO_HYBRID_TAIL
+    sum_tile<D, NC, P, L>(a, b * kTile, s_rec, s_bar);
+#else
+    if (P == 1 || L > 1 || b < a.n_big) {
+        sum_tile<D, NC, P, L>(a, b * kTile, s_rec, s_bar);
+    } else {
+        sum_tile<D, NC, 1, (P == 1 ? L : 1)>(a, a.n_big * kTile + (b - a.n_big) * kThreads, s_rec, s_bar);
+    }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------

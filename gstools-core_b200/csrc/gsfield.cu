@@ -317,7 +317,7 @@ int validate(const Problem &p)
 // Table from tools/variant_sweep.py on B200 (N = 1000, all kinds/dims):
 //   * below ~750k points P = 1 wins (most CTAs per SM => best balance across the 148 SMs);
 //   * above, P = 3 amortises the LDS/loop instructions that steal issue cycles from the FP64
-//     pipe (2-D scalar: P = 2 up to 2M points, P = 4 beyond);
+//     pipe, with the last half resident wave in short P = 1 tiles (launch_sum);
 //   * fewer than 2 CTAs per SM: split the modes over L lanes of a point group so that every SM
 //     gets work (keep >= 16 modes per lane).
 void choose_variant(const DeviceCtx &d, const Problem &p, int64_t m_launch, int *P, int *L)
@@ -339,7 +339,6 @@ void choose_variant(const DeviceCtx &d, const Problem &p, int64_t m_launch, int 
     int bestP = 1, bestL = 1;
     if (m_launch >= 750000) {
         bestP = 3;
-        if (!inc && p.dim == 2) bestP = m_launch >= 2000000 ? 4 : 2;
     } else if (ctas1 < 2 * d.sm_count) {
         while (bestL < 32 && ctas1 * bestL < 2 * d.sm_count && p.N >= 32 * bestL) bestL *= 2;
     }
@@ -359,8 +358,27 @@ int launch_sum(DeviceCtx &d, const Problem &p, const double *kpos, int64_t ps0, 
     a.n_points = m;
     a.out = kout; a.os0 = os0; a.os1 = os1;
     for (int c = 0; c < 3; ++c) a.offset[c] = p.offset[c];
+    {
+        static const double u[8] = {GSF_U0, GSF_U1, GSF_U2, GSF_U3, GSF_U4, GSF_U5, GSF_U6, 0.0};
+        for (int c = 0; c < 8; ++c) a.coef[c] = u[c];
+    }
+    // long tiles (P points per thread) first, then short tiles (1 point per thread) for the last
+    // `tail` resident waves so that the machine drains in small steps (see gsf_sum_kernel)
     const int64_t tile = (int64_t)P * (kThreads / L);
-    const int64_t grid = (m + tile - 1) / tile;
+    int64_t n_big = (m + tile - 1) / tile, n_small = 0;
+    if (P > 1 && L == 1) {
+        static const double tail_waves = []() {
+            const char *e = getenv("GSF_TAIL_WAVES");
+            return e && *e ? atof(e) : 0.5;
+        }();
+        const int64_t resident = (int64_t)d.sm_count * 8;                  // ~CTAs in flight
+        int64_t tail_pts = (int64_t)(tail_waves * (double)resident * (double)tile);
+        tail_pts = std::min(tail_pts, m);
+        n_big = (m - tail_pts) / tile;
+        n_small = (m - n_big * tile + kThreads - 1) / kThreads;
+    }
+    a.n_big = n_big;
+    const int64_t grid = n_big + n_small;
     if (grid > 0x7fffffffLL) return fail(GSF_ERR_SHAPE, "chunk of %lld points is too large for one launch", (long long)m);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (ctx().profiling) {
