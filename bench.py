@@ -354,6 +354,14 @@ def run_ours(args):
         return
 
     peaks = peak_file()
+    traffic = None
+    if args.workload == "c2" and args.scale == 1.0:
+        try:   # DRAM bytes per launch from the committed ncu --set full capture of this kernel
+            with open(os.path.join(ROOT, "profiles", "ncu_r1_c2_traffic.json")) as f:
+                t = json.load(f)
+            traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
+        except Exception:
+            traffic = None
     w_exec = workloads.W_EXEC[args.workload]
     w_survey = workloads.W_SURVEY[args.workload]
     pm_per_s_kernel = pm / (kernel_ms * 1e-3)
@@ -380,7 +388,8 @@ def run_ours(args):
         "gpu_launches": launches + e2e_launches,
         "roofline": {
             "bound": "fp64", "achieved": ach_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
-            "frac": ach_tflops / peak_tflops, "traffic": None,
+            "frac": ach_tflops / peak_tflops, "traffic": traffic,
+            "traffic_unit": "bytes of DRAM per launch (ncu dram__bytes_read+write); algorithmic bytes: %d" % (pos_bytes + out_bytes),
             "kernel": "gsf_sum_kernel", "kernel_ms": kernel_ms,
             "fp64_slots_per_point_mode": w_exec,
             "peak_source": "gsf_dfma_peak measured in this run: %.2f T DFMA/s over %.0f ms (of measured)"
