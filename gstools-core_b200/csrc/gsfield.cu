@@ -320,7 +320,7 @@ int validate(const Problem &p)
 //     pipe, with the last half resident wave in short P = 1 tiles (launch_sum);
 //   * fewer than 2 CTAs per SM: split the modes over L lanes of a point group so that every SM
 //     gets work (keep >= 16 modes per lane).
-void choose_variant(const DeviceCtx &d, const Problem &p, int64_t m_launch, int *P, int *L)
+void choose_variant(const DeviceCtx &d, const Problem &p, int64_t m_launch, bool pipelined, int *P, int *L)
 {
     Context &c = ctx();
     const bool inc = p.kind == gsf::kIncompr;
@@ -337,7 +337,9 @@ void choose_variant(const DeviceCtx &d, const Problem &p, int64_t m_launch, int 
         return;
     }
     int bestP = 1, bestL = 1;
-    if (m_launch >= 750000) {
+    // a pipelined chunk is followed by the next chunk's kernel on another stream, which fills the
+    // SMs as this one drains: long tiles pay off from much smaller launches
+    if (m_launch >= (pipelined ? 120000 : 750000)) {
         bestP = 3;
     } else if (ctas1 < 2 * d.sm_count) {
         while (bestL < 32 && ctas1 * bestL < 2 * d.sm_count && p.N >= 32 * bestL) bestL *= 2;
@@ -614,6 +616,37 @@ void scatter_out(const Problem &p, const OutLayout &lay, int64_t j0, int64_t cnt
     });
 }
 
+// Chunk sizes for streaming m points through the pipeline slots (see run_shard).
+std::vector<int64_t> chunk_schedule(int64_t m, bool single_launch, int64_t forced_chunk)
+{
+    std::vector<int64_t> sizes;
+    if (m <= 0) return sizes;
+    if (single_launch) {
+        sizes.push_back(m);
+    } else if (forced_chunk > 0) {
+        const int64_t chunk = std::min((forced_chunk + 1023) / 1024 * 1024, m);
+        for (int64_t done = 0; done < m; done += chunk) sizes.push_back(std::min(chunk, m - done));
+    } else {
+        const int64_t lo = 1 << 15;
+        int64_t cap = std::min<int64_t>(1 << 20, std::max<int64_t>(1 << 16, m / 6));
+        cap = cap / 1024 * 1024;
+        std::vector<int64_t> up, down;
+        int64_t used = 0;
+        for (int64_t c = lo; c < cap && used + c + c / 2 <= m / 2; c *= 2) { up.push_back(c); used += c; }
+        for (int64_t c = lo; c < cap && used + c + c / 2 <= m * 3 / 4; c *= 2) { down.push_back(c); used += c; }
+        int64_t rest = m - used;
+        sizes = up;
+        while (rest > 0) {
+            int64_t c = std::min(cap, rest);
+            if (rest - c > 0 && rest - c < lo) c = rest;          // do not leave a tiny remainder
+            sizes.push_back(c);
+            rest -= c;
+        }
+        for (size_t i = down.size(); i-- > 0;) sizes.push_back(down[i]);
+    }
+    return sizes;
+}
+
 // Process points [j_beg, j_end) of the problem on device d (host- or device-resident pos/out).
 int run_shard(DeviceCtx &d, const Problem &p, int64_t j_beg, int64_t j_end, int pos_kind, int out_kind,
               int *P_used, int *L_used, int host_threads)
@@ -631,39 +664,38 @@ int run_shard(DeviceCtx &d, const Problem &p, int64_t j_beg, int64_t j_end, int 
     for (int s = 1; s < kSlots; ++s) GSF_CUDA(cudaStreamWaitEvent(d.slot[s].stream, d.ev_modes, 0));
 
     const bool pos_dev = pos_kind == 2, out_dev = out_kind == 2;
-    // chunking: device-resident both ways => one launch; otherwise pipeline chunks
-    int64_t chunk = m_shard;
-    if (!(pos_dev && out_dev)) {
-        chunk = ctx().chunk_points;
-        if (chunk <= 0) {
-            chunk = (m_shard + 15) / 16;
-            chunk = std::max<int64_t>(chunk, 1 << 15);
-            chunk = std::min<int64_t>(chunk, 1 << 20);
-        }
-        chunk = (chunk + 1023) / 1024 * 1024;
-        chunk = std::min(chunk, std::max<int64_t>(m_shard, 1));
-    }
-    const int64_t n_chunks = m_shard > 0 ? (m_shard + chunk - 1) / chunk : 0;
+    // Chunk schedule.  Device-resident both ways => one launch.  Otherwise the points stream through
+    // the three pipeline slots: the first chunks are small and double in size (the first kernel
+    // starts after a ~0.8 MB copy instead of waiting for megabytes), the middle runs at `cap`
+    // points per chunk (long kernels, P = 3 tiles), and the last chunks halve again so that little
+    // D2H is left exposed after the final kernel.  gsf_set_chunk_points(n) forces a fixed size.
+    std::vector<int64_t> sizes = chunk_schedule(m_shard, pos_dev && out_dev, ctx().chunk_points);
+    const int64_t n_chunks = (int64_t)sizes.size();
+    int64_t chunk = 0;
+    for (int64_t c : sizes) chunk = std::max(chunk, c);
 
     const bool direct_in = pos_kind == 1 && p.ps1 == 1;
     OutLayout lay;
     lay.aos = nc > 1 && p.os0 == 1 && p.os1 == nc;
     lay.direct = out_kind == 1 && (nc == 1 ? p.os1 == 1 : (lay.aos || p.os1 == 1));
 
-    int P = 2, L = 1;
-    choose_variant(d, p, std::min(chunk, m_shard), &P, &L);
+    int P = 1, L = 1;
+    const bool pipelined = n_chunks > 1;
+    choose_variant(d, p, std::min(chunk, m_shard), pipelined, &P, &L);
     *P_used = P;
     *L_used = L;
 
     struct Pending { int64_t j0, cnt; bool live; } pend[kSlots] = {};
     bool slot_in_used[kSlots] = {false, false, false};
 
+    int64_t j_next = j_beg;
     for (int64_t c = 0; c < n_chunks; ++c) {
         const int si = (int)(c % kSlots);
         Slot &sl = d.slot[si];
         cudaStream_t st = sl.stream;
-        const int64_t j0 = j_beg + c * chunk;
-        const int64_t cnt = std::min(chunk, j_end - j0);
+        const int64_t j0 = j_next;
+        const int64_t cnt = sizes[(size_t)c];
+        j_next += cnt;
 
         // drain the staging-out buffer of the chunk that used this slot last
         if (pend[si].live) {
@@ -712,7 +744,9 @@ int run_shard(DeviceCtx &d, const Problem &p, int64_t j_beg, int64_t j_end, int 
             kout = sl.d_out;
             if (lay.aos) { kos0 = 1; kos1 = nc; } else { kos0 = cnt; kos1 = 1; }
         }
-        if ((rc = launch_sum(d, p, kpos, kps0, kps1, kout, kos0, kos1, cnt, st, P, L))) return rc;
+        int Pc = P, Lc = L;
+        if (cnt != chunk) choose_variant(d, p, cnt, pipelined, &Pc, &Lc);
+        if ((rc = launch_sum(d, p, kpos, kps0, kps1, kout, kos0, kos1, cnt, st, Pc, Lc))) return rc;
 
         // ---- output
         if (!out_dev) {
@@ -1081,7 +1115,7 @@ int gsf_summate_on_stream(int kind, int dim, int64_t n_modes, int64_t n_points, 
     if (d->ws_used) GSF_CUDA(cudaStreamWaitEvent(st, d->ev_ws, 0));
     if ((rc = prepare_modes(*d, p, st))) return rc;
     int P, L;
-    choose_variant(*d, p, p.M, &P, &L);
+    choose_variant(*d, p, p.M, false, &P, &L);
     if ((rc = launch_sum(*d, p, p.pos, p.ps0, p.ps1, p.out, p.os0, p.os1, p.M, st, P, L))) return rc;
     GSF_CUDA(cudaEventRecord(d->ev_ws, st));
     d->ws_used = true;
@@ -1117,6 +1151,28 @@ int gsf_summate_ex(const gsf_request *r)
         return run_host_call(p, &g);
     }
     return run_host_call(p, nullptr);
+}
+
+/* Host-logic introspection (used by the CPU test-suite; no device needed). */
+int gsf_debug_chunk_schedule(int64_t n_points, int64_t forced_chunk, int64_t *sizes, int max_sizes)
+{
+    if (n_points < 0 || !sizes || max_sizes < 1) return fail(GSF_ERR_ARG, "bad arguments");
+    const std::vector<int64_t> v = chunk_schedule(n_points, false, forced_chunk);
+    const int n = (int)std::min<size_t>(v.size(), (size_t)max_sizes);
+    for (int i = 0; i < n; ++i) sizes[i] = v[(size_t)i];
+    return (int)v.size() > max_sizes ? -(int)v.size() : n;
+}
+
+int gsf_debug_detect_grid(int dim, int64_t n_points, const double *pos, int64_t pos_s0, int64_t pos_s1,
+                          int64_t *axis_n)
+{
+    if (!pos || !axis_n) return fail(GSF_ERR_ARG, "bad arguments");
+    Problem p{};
+    p.dim = dim; p.M = n_points; p.pos = pos; p.ps0 = pos_s0; p.ps1 = pos_s1;
+    GridSpec g;
+    if (!detect_grid_host(p, &g, staging_threads(0, 1))) return 0;
+    for (int a = 0; a < 3; ++a) axis_n[a] = a < dim ? g.n[a] : 1;
+    return 1;
 }
 
 int gsf_set_grid_detection(int enabled)

@@ -132,6 +132,13 @@ int gsf_summate_ex(const gsf_request *request);
 /* 1 / 0: enable / disable automatic structured-grid detection; -1: follow GSF_GRID_DETECT (default on). */
 int gsf_set_grid_detection(int enabled);
 
+/* Host-logic introspection for tests (no device needed): the pipeline chunk sizes for n_points
+ * host-resident points (returns the count, or -count if max_sizes is too small), and the exact
+ * structured-grid detector (returns 1 and the axis lengths, or 0). */
+int gsf_debug_chunk_schedule(int64_t n_points, int64_t forced_chunk, int64_t *sizes, int max_sizes);
+int gsf_debug_detect_grid(int dim, int64_t n_points, const double *pos, int64_t pos_s0, int64_t pos_s1,
+                          int64_t *axis_n);
+
 /* ---- stream-ordered variant for device-resident data -------------------------------------- */
 
 /* kind: 0 summate, 1 summate_incompr, 2 summate_fourier.  pos and out must be device pointers on
