@@ -554,7 +554,11 @@ int staging_threads(int hint, int n_devices)
 {
     if (n_devices > 1) return 1;   // one staging thread per device already
     int hw = (int)std::thread::hardware_concurrency();
-    int t = std::max(1, std::min(8, hw / 2));
+    // measured on the 16-vCPU B200 host (tools/pageable_probe.py): 2 threads beat 1, 4, 8 and 16 --
+    // condition-variable wake-ups of more workers cost more than the extra memcpy bandwidth buys
+    int t = hw >= 4 ? 2 : 1;
+    static const int env_t = []() { const char *e = getenv("GSF_STAGING_THREADS"); return e && *e ? atoi(e) : 0; }();
+    if (env_t > 0) t = env_t;
     if (hint > 0) t = std::min(t, hint);
     return t;
 }
@@ -674,7 +678,9 @@ int run_shard(DeviceCtx &d, const Problem &p, int64_t j_beg, int64_t j_end, int 
     int64_t chunk = 0;
     for (int64_t c : sizes) chunk = std::max(chunk, c);
 
-    const bool direct_in = pos_kind == 1 && p.ps1 == 1;
+    // GSF_PAGEABLE_DIRECT=1: hand pageable memory straight to cudaMemcpyAsync (the driver stages it)
+    static const bool pageable_direct = []() { const char *e = getenv("GSF_PAGEABLE_DIRECT"); return e && e[0] == '1'; }();
+    const bool direct_in = (pos_kind == 1 || (pageable_direct && pos_kind == 0)) && p.ps1 == 1;
     OutLayout lay;
     lay.aos = nc > 1 && p.os0 == 1 && p.os1 == nc;
     lay.direct = out_kind == 1 && (nc == 1 ? p.os1 == 1 : (lay.aos || p.os1 == 1));

@@ -1,0 +1,137 @@
+// Experiment: mode records read from __constant__ memory (LDCU -> uniform registers) instead of
+// shared memory, so the mode operands of the DFMAs do not use register-file read ports.
+#include <cstdio>
+#include <vector>
+#include <random>
+#include "../../gstools-core_b200/csrc/gsf_kernels.cuh"
+
+__constant__ double c_modes[8184];
+
+template <int D, int NC, int P, int U>
+__global__ void __launch_bounds__(128) sum_const(gsf::SumArgs a, int n_modes)
+{
+    using namespace gsf;
+    constexpr int R = rec_doubles(D, NC);
+    const int tid = threadIdx.x;
+    const int64_t tile0 = (int64_t)blockIdx.x * (128 * P);
+    double x[P][D];
+    int64_t jpt[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        const int64_t j = tile0 + (int64_t)p * 128 + tid;
+        jpt[p] = j;
+        const int64_t jc = j < a.n_points ? j : a.n_points - 1;
+#pragma unroll
+        for (int d = 0; d < D; ++d) x[p][d] = __ldg(a.pos + d * a.ps0 + jc * a.ps1);
+    }
+    double acc[P][NC];
+#pragma unroll
+    for (int p = 0; p < P; ++p)
+#pragma unroll
+        for (int c = 0; c < NC; ++c) acc[p][c] = 0.0;
+    const PolyCoef coef = {a.coef[0], a.coef[1], a.coef[2], a.coef[3], a.coef[4], a.coef[5], a.coef[6]};
+#pragma unroll U
+    for (int i = 0; i < n_modes; ++i) {
+        const double *m = c_modes + i * R;
+        double kh[D], nth, amp[NC];
+#pragma unroll
+        for (int d = 0; d < D; ++d) kh[d] = m[d];
+        nth = m[D];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) amp[c] = m[D + 1 + c];
+        double t[P], tn[P], sq[P], u[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) t[p] = fma(kh[0], x[p][0], nth);
+#pragma unroll
+        for (int d = 1; d < D; ++d)
+#pragma unroll
+            for (int p = 0; p < P; ++p) t[p] = fma(kh[d], x[p][d], t[p]);
+#pragma unroll
+        for (int p = 0; p < P; ++p) tn[p] = __dadd_rn(t[p], kMagic);
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const double nf = __dadd_rn(tn[p], -kMagic);
+            const double r = __dadd_rn(t[p], -nf);
+            sq[p] = __dmul_rn(r, r);
+        }
+#pragma unroll
+        for (int p = 0; p < P; ++p) u[p] = fma(coef.c6, sq[p], coef.c5);
+#pragma unroll
+        for (int p = 0; p < P; ++p) u[p] = fma(u[p], sq[p], coef.c4);
+#pragma unroll
+        for (int p = 0; p < P; ++p) u[p] = fma(u[p], sq[p], coef.c3);
+#pragma unroll
+        for (int p = 0; p < P; ++p) u[p] = fma(u[p], sq[p], coef.c2);
+#pragma unroll
+        for (int p = 0; p < P; ++p) u[p] = fma(u[p], sq[p], coef.c1);
+#pragma unroll
+        for (int p = 0; p < P; ++p) u[p] = fma(u[p], sq[p], coef.c0);
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const double y = fma(u[p], u[p], -1.0);
+            const uint32_t hi = static_cast<uint32_t>(__double2hiint(y)) + (static_cast<uint32_t>(__double2loint(tn[p])) << 31);
+            u[p] = __hiloint2double(static_cast<int>(hi), __double2loint(y));
+        }
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+#pragma unroll
+            for (int p = 0; p < P; ++p) acc[p][c] = fma(amp[c], u[p], acc[p][c]);
+    }
+#pragma unroll
+    for (int p = 0; p < P; ++p)
+        if (jpt[p] < a.n_points)
+#pragma unroll
+            for (int c = 0; c < NC; ++c) a.out[c * a.os0 + jpt[p] * a.os1] = acc[p][c];
+}
+
+template <int D, int NC, int P, int U>
+double run(int64_t m, int n_modes)
+{
+    using namespace gsf;
+    constexpr int R = rec_doubles(D, NC);
+    std::mt19937_64 rng(1);
+    std::normal_distribution<double> nd;
+    std::uniform_real_distribution<double> ud(0, 100);
+    std::vector<double> rec((size_t)n_modes * R, 0.0), pos((size_t)D * m);
+    for (int i = 0; i < n_modes; ++i) {
+        for (int d = 0; d < D; ++d) rec[(size_t)i * R + d] = nd(rng) / 3.14159;
+        rec[(size_t)i * R + D] = ud(rng) / 100.0;
+        for (int c = 0; c < NC; ++c) rec[(size_t)i * R + D + 1 + c] = nd(rng);
+    }
+    for (auto &v : pos) v = ud(rng);
+    double *dpos, *dout;
+    cudaMalloc(&dpos, pos.size() * 8); cudaMalloc(&dout, (size_t)NC * m * 8);
+    cudaMemcpyToSymbol(c_modes, rec.data(), rec.size() * 8);
+    cudaMemcpy(dpos, pos.data(), pos.size() * 8, cudaMemcpyHostToDevice);
+    SumArgs a{};
+    a.n_modes = n_modes; a.pos = dpos; a.ps0 = m; a.ps1 = 1; a.n_points = m; a.out = dout; a.os0 = 1; a.os1 = NC;
+    const double u[8] = {GSF_U0, GSF_U1, GSF_U2, GSF_U3, GSF_U4, GSF_U5, GSF_U6, 0};
+    for (int c = 0; c < 8; ++c) a.coef[c] = u[c];
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e9f;
+    const int64_t grid = (m + 128 * P - 1) / (128 * P);
+    for (int it = 0; it < 6; ++it) {
+        cudaEventRecord(e0);
+        sum_const<D, NC, P, U><<<(unsigned)grid, 128>>>(a, n_modes);
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (it >= 1 && ms < best) best = ms;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) printf("CUDA error %s\n", cudaGetErrorString(e));
+    cudaFree(dpos); cudaFree(dout);
+    return (double)m * n_modes / best / 1e6;
+}
+
+int main()
+{
+    printf("const-mem modes, d3 scalar, N=1000 (no tail trick): \n");
+    printf(" P3 U1: 1M %.0f 4M %.0f\n", run<3, 1, 3, 1>(1000000, 1000), run<3, 1, 3, 1>(4000000, 1000));
+    printf(" P3 U2: 1M %.0f 4M %.0f\n", run<3, 1, 3, 2>(1000000, 1000), run<3, 1, 3, 2>(4000000, 1000));
+    printf(" P3 U4: 1M %.0f 4M %.0f\n", run<3, 1, 3, 4>(1000000, 1000), run<3, 1, 3, 4>(4000000, 1000));
+    printf(" P2 U2: 1M %.0f 4M %.0f\n", run<3, 1, 2, 2>(1000000, 1000), run<3, 1, 2, 2>(4000000, 1000));
+    printf(" P4 U2: 1M %.0f 4M %.0f\n", run<3, 1, 4, 2>(1000000, 1000), run<3, 1, 4, 2>(4000000, 1000));
+    printf(" P1 U4: 1M %.0f 4M %.0f\n", run<3, 1, 1, 4>(1000000, 1000), run<3, 1, 1, 4>(4000000, 1000));
+    printf(" incompr P3 U2: 4M %.0f   d2 P3 U2: 4M %.0f\n", run<3, 3, 3, 2>(4000000, 1000), run<2, 1, 3, 2>(4000000, 1000));
+    return 0;
+}
