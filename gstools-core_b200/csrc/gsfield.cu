@@ -939,8 +939,8 @@ int run_host_call(Problem p, const GridSpec *grid)
         p.dim = grid->dim;
         p.M = grid->points();
         for (int a = 0; a < grid->dim; ++a)
-            if (grid->n[a] < 1 || !grid->axis[a]) return fail(GSF_ERR_SHAPE, "bad grid axis %d", a);
-        p.pos = grid->axis[0];   // placeholder so validate() sees a non-NULL pointer
+            if (grid->n[a] < 0 || (grid->n[a] > 0 && !grid->axis[a])) return fail(GSF_ERR_SHAPE, "bad grid axis %d", a);
+        p.pos = p.out;           // placeholder so validate() sees a non-NULL pointer (pos is unused)
     }
     int rc = validate(p);
     if (rc) return rc;
@@ -987,9 +987,16 @@ int run_host_call(Problem p, const GridSpec *grid)
     GridSpec detected;
     const GridSpec *gs = grid;
     const int threads1 = staging_threads(p.threads_hint, 1);
-    if (!gs && pos_kind != 2 && p.N >= 32 && grid_detection_enabled() &&
-        detect_grid_host(p, &detected, threads1) && detected.rows() >= 16)
-        gs = &detected;
+    // Worth it only when the general kernel would take longer than the grid path's fixed cost
+    // (~5 extra launches, tools/latency_sweep.py: break-even near 2e7 point*modes) and when the
+    // per-axis tables stay small next to HBM.
+    if (!gs && pos_kind != 2 && p.N >= 32 && (double)p.M * (double)p.N >= 2e7 && grid_detection_enabled() &&
+        detect_grid_host(p, &detected, threads1) && detected.rows() >= 16) {
+        const double table_bytes = 16.0 * (double)(p.N + 16) *
+                                   ((double)detected.n[0] + (detected.dim == 3 ? (double)detected.n[1] : 0.0) +
+                                    (double)detected.n_last() * p.nc());
+        if (table_bytes <= 8e9) gs = &detected;
+    }
 
     int P = 0, L = 0;
     if (gs) {

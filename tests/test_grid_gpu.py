@@ -99,8 +99,10 @@ def test_auto_detection_matches_general_kernel():
 def test_detection_rejects_non_grids():
     axes = [np.linspace(0, 50, 41), np.linspace(-5, 5, 37), np.linspace(2, 9, 64)]
     pos = expand(axes)
-    k, z1, z2, _ = modes(6, 3, 64)
+    k, z1, z2, _ = modes(6, 3, 256)
     gc.set_grid_detection(True)
+    gc.summate(k, z1, z2, pos)
+    assert gc.last_stats()["grid_path"] == 1                       # the unmodified grid is detected
     for mutate in (lambda p: p.__setitem__((2, 12345), p[2, 12345] + 1e-13),     # one perturbed point
                    lambda p: p.__setitem__((0, -1), np.nextafter(p[0, -1], 1e9)),
                    lambda p: p.__setitem__((1, 64 * 5 + 3), -p[1, 64 * 5 + 3] - 1.0)):
@@ -121,6 +123,31 @@ def test_detection_rejects_non_grids():
     posxy = np.ascontiguousarray(np.stack([g.ravel() for g in gx]))
     got = gc.summate(k, z1, z2, posxy)
     assert rel_err(got, oracle.summate(k, z1, z2, posxy, oracle.max_threads())) <= TOL
+
+
+def test_grid_edge_cases():
+    k, z1, z2, sf = modes(9, 3, 50)
+    # empty grid: one axis of length 0
+    out = gc.summate_grid(k, z1, z2, [np.linspace(0, 1, 5), np.zeros(0), np.linspace(0, 1, 7)])
+    assert out.shape == (0,)
+    # single-point axes, N = 0 (fold identity), NaN mode, zero mode in incompr
+    axes = [np.array([1.5]), np.linspace(0, 1, 40), np.linspace(0, 2, 33)]
+    pos = expand(axes)
+    assert rel_err(gc.summate_grid(k, z1, z2, axes), oracle.summate(k, z1, z2, pos)) <= TOL
+    z0 = np.zeros(0)
+    assert np.array_equal(gc.summate_grid(np.zeros((3, 0)), z0, z0, axes), np.zeros(pos.shape[1]))
+    kn = k.copy(); kn[1, 7] = np.nan
+    assert np.isnan(gc.summate_grid(kn, z1, z2, axes)).all()
+    kz = k.copy(); kz[:, 3] = 0.0
+    assert np.isnan(gc.summate_incompr_grid(kz, z1, z2, axes)).all()       # 0/0 as in the reference
+    with pytest.raises(ValueError):
+        gc.summate_incompr_grid(np.zeros((3, 0)), z0, z0, axes)             # field.rs:163
+    with pytest.raises(ValueError):
+        gc.summate_grid(k, z1, z2, axes[:2])                               # axis count != dim
+    # an infinite coordinate poisons exactly the points that use it
+    ax = [np.linspace(0, 1, 20), np.array([0.0, np.inf, 1.0]), np.linspace(0, 1, 16)]
+    out = gc.summate_grid(k, z1, z2, ax).reshape(20, 3, 16)
+    assert np.isnan(out[:, 1, :]).all() and np.isfinite(out[:, 0, :]).all() and np.isfinite(out[:, 2, :]).all()
 
 
 def test_scale_and_offset_fusion():
