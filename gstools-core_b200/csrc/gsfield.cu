@@ -290,6 +290,7 @@ struct Problem {
     const double *pos; int64_t ps0, ps1;
     double *out; int64_t os0, os1;
     int threads_hint = 0;
+    int peer_owner = -1;                 // >= 0: device arrays live on this device, peers may read them
     double scale = 1.0;                  // out = scale * sum + offset[a]   
     double offset[3] = {0.0, 0.0, 0.0};
     int nc() const { return kind == gsf::kIncompr ? dim : 1; }
@@ -341,7 +342,9 @@ void choose_variant(const DeviceCtx &d, const Problem &p, int64_t m_launch, bool
     // SMs as this one drains: long tiles pay off from much smaller launches
     if (m_launch >= (pipelined ? 120000 : 750000)) {
         bestP = 3;
-    } else if (ctas1 < 2 * d.sm_count) {
+    } else if (ctas1 < 2 * d.sm_count && !pipelined) {
+        // (pipelined chunks never split the modes: neighbouring chunks' kernels fill the machine,
+        //  and L = 1 keeps every point's summation order independent of chunking / device count)
         while (bestL < 32 && ctas1 * bestL < 2 * d.sm_count && p.N >= 32 * bestL) bestL *= 2;
     }
     *P = bestP;
@@ -428,7 +431,8 @@ int prepare_modes(DeviceCtx &d, const Problem &p, cudaStream_t st)
     a.scale = p.scale;
     a.rec = d.d_rec;
     if (all_dev) {
-        if (kd != d.dev) return fail(GSF_ERR_ARG, "mode arrays live on device %d, work runs on device %d", kd, d.dev);
+        if (kd != d.dev && kd != p.peer_owner)
+            return fail(GSF_ERR_ARG, "mode arrays live on device %d, work runs on device %d", kd, d.dev);
         a.k = p.k; a.ks0 = p.ks0; a.ks1 = p.ks1;
         a.z1 = p.z1; a.z1s = p.z1s;
         a.z2 = p.z2; a.z2s = p.z2s;
@@ -894,6 +898,28 @@ std::vector<int> default_devices()
     return v;
 }
 
+// Let kernels running on `dev` load/store memory that lives on `owner` (NVLink peer mapping).
+bool enable_peer(int dev, int owner)
+{
+    if (dev == owner) return true;
+    int can = 0;
+    if (cudaDeviceCanAccessPeer(&can, dev, owner) != cudaSuccess || !can) {
+        cudaGetLastError();
+        return false;
+    }
+    if (cudaSetDevice(dev) != cudaSuccess) return false;
+    cudaError_t e = cudaDeviceEnablePeerAccess(owner, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) {
+        cudaGetLastError();
+        return true;
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return true;
+}
+
 void collect_stats(const Problem &p, const std::vector<DeviceCtx *> &used, double total_ms, int P, int L,
                    int pos_kind, int out_kind, int grid_path)
 {
@@ -967,12 +993,29 @@ int run_host_call(Problem p, const GridSpec *grid)
     std::vector<int> devs = c.devices_explicit ? c.devices : default_devices();
     for (int id : devs)
         if (id < 0 || id >= ndev_visible) return fail(GSF_ERR_ARG, "configured device %d not visible (%d devices)", id, ndev_visible);
+    bool peer_shards = false;
     if (pos_kind == 2 || out_kind == 2) {
-        // device-resident data pins the work to that device
+        // device-resident data: the work runs where the data lives ...
         const int dv = pos_kind == 2 ? pos_dev : out_dev;
         if (pos_kind == 2 && out_kind == 2 && pos_dev != out_dev)
             return fail(GSF_ERR_ARG, "pos on device %d but out on device %d", pos_dev, out_dev);
-        devs.assign(1, dv);
+        // ... unless several devices were configured explicitly and both pos and out are device
+        // resident: then every configured device takes a contiguous point shard and reads its
+        // positions / writes its results directly in the owner's memory over NVLink (peer
+        // mapping) -- no staging copies, no collective.
+        bool ok = c.devices_explicit && devs.size() > 1 && pos_kind == 2 && out_kind == 2 && !grid;
+        if (ok) {
+            bool has_owner = false;
+            for (int id : devs) has_owner |= id == dv;
+            ok = has_owner;
+            for (int id : devs) ok = ok && enable_peer(id, dv);
+        }
+        if (ok) {
+            peer_shards = true;
+            p.peer_owner = dv;
+        } else {
+            devs.assign(1, dv);
+        }
     }
     // do not spread tiny problems: at least 2^16 points per device
     int G = (int)devs.size();

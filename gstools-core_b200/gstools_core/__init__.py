@@ -376,7 +376,7 @@ def set_grid_detection(enabled=True):
 # ---------------------------------------------------------------------------------------------
 # device-resident, stream-ordered entry points
 
-def _on_stream(kind, sf, cov_samples, z1, z2, pos, out, stream):
+def _on_stream(kind, sf, cov_samples, z1, z2, pos, out, stream, sync=False):
     L = _load()
     cov, a1, a2, p = _Arr(cov_samples, 2, "cov_samples"), _Arr(z1, 1, "z1"), _Arr(z2, 1, "z2"), _Arr(pos, 2, "pos")
     _check_shapes(cov, a1, a2, p)
@@ -400,24 +400,40 @@ def _on_stream(kind, sf, cov_samples, z1, z2, pos, out, stream):
         sargs = s.args()
     else:
         sargs = (None, 0)
-    rc = L.gsf_summate_on_stream(kind, d, n, m, *sargs, *cov.args(), *a1.args(), *a2.args(), *p.args(),
-                                 o.ptr, ostr[0], ostr[1], _vp(int(stream) if stream else 0))
+    if sync:
+        # synchronous host-style entry points with device pointers: returns when the result is
+        # complete, and shards the points over set_devices([...]) through NVLink peer mappings
+        if kind == 0:
+            rc = L.gsf_summate(d, n, m, *cov.args(), *a1.args(), *a2.args(), *p.args(), o.ptr, 0)
+        elif kind == 1:
+            rc = L.gsf_summate_incompr(d, n, m, *cov.args(), *a1.args(), *a2.args(), *p.args(), o.ptr,
+                                       ostr[0], ostr[1], 0)
+        else:
+            rc = L.gsf_summate_fourier(d, n, m, *sargs, *cov.args(), *a1.args(), *a2.args(), *p.args(), o.ptr, 0)
+    else:
+        rc = L.gsf_summate_on_stream(kind, d, n, m, *sargs, *cov.args(), *a1.args(), *a2.args(), *p.args(),
+                                     o.ptr, ostr[0], ostr[1], _vp(int(stream) if stream else 0))
     if rc:
         _raise(rc)
     return out
 
 
-def summate_device(cov_samples, z1, z2, pos, out, stream=0):
-    """summate on device-resident pos/out, enqueued on `stream` (a cudaStream_t handle); no sync."""
-    return _on_stream(0, None, cov_samples, z1, z2, pos, out, stream)
+def summate_device(cov_samples, z1, z2, pos, out, stream=0, sync=False):
+    """summate on device-resident pos/out.
+
+    sync=False: enqueued on `stream` (a cudaStream_t handle) of the arrays' device, no host sync.
+    sync=True : blocking call; with set_devices([...]) naming several GPUs every device takes a
+                contiguous point shard and reads/writes the owner's memory over NVLink (peer
+                mapping), no staging copies and no collective."""
+    return _on_stream(0, None, cov_samples, z1, z2, pos, out, stream, sync)
 
 
-def summate_incompr_device(cov_samples, z1, z2, pos, out, stream=0):
-    return _on_stream(1, None, cov_samples, z1, z2, pos, out, stream)
+def summate_incompr_device(cov_samples, z1, z2, pos, out, stream=0, sync=False):
+    return _on_stream(1, None, cov_samples, z1, z2, pos, out, stream, sync)
 
 
-def summate_fourier_device(spectrum_factor, modes, z1, z2, pos, out, stream=0):
-    return _on_stream(2, spectrum_factor, modes, z1, z2, pos, out, stream)
+def summate_fourier_device(spectrum_factor, modes, z1, z2, pos, out, stream=0, sync=False):
+    return _on_stream(2, spectrum_factor, modes, z1, z2, pos, out, stream, sync)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -304,3 +304,31 @@ def test_multi_device_sharding_matches_single():
     assert gc.last_stats()["n_devices"] == min(gc.device_count(), 400_000 // 65536)
     assert np.array_equal(one, many)              # per-point mode order does not depend on the shard
     assert np.array_equal(onei, gc.summate_incompr(k, z1, z2, pos))
+
+
+def test_peer_sharding_of_device_resident_data():
+    """pos/out resident on GPU 0, points sharded over all GPUs through NVLink peer
+    mappings (kernels on GPU g read positions from / write results to GPU 0 directly)."""
+    torch = pytest.importorskip("torch")
+    if gc.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    k, z1, z2, pos = _rand(61, 3, 300, 600_000, heavy=True)
+    dpos = torch.from_numpy(pos).cuda(0)
+    dk, dz1, dz2 = (torch.from_numpy(x).cuda(0) for x in (k, z1, z2))
+    one = torch.empty(pos.shape[1], dtype=torch.float64, device="cuda:0")
+    many = torch.empty_like(one)
+    torch.cuda.synchronize()
+    gc.set_devices([0])
+    gc.summate_device(k, z1, z2, dpos, one, sync=True)
+    assert gc.last_stats()["n_devices"] == 1
+    gc.set_devices(list(range(gc.device_count())))
+    gc.summate_device(k, z1, z2, dpos, many, sync=True)
+    assert gc.last_stats()["n_devices"] == min(gc.device_count(), 600_000 // 65536)
+    assert torch.equal(one, many)
+    ref = oracle.summate(k, z1, z2, pos, oracle.max_threads())
+    assert rel_err(many.cpu().numpy(), ref) <= TOL
+    # modes resident on the owner too, incompressible field with F-ordered output
+    outi = torch.empty((pos.shape[1], 3), dtype=torch.float64, device="cuda:0").t()
+    gc.summate_incompr_device(dk, dz1, dz2, dpos, outi, sync=True)
+    assert gc.last_stats()["n_devices"] > 1
+    assert rel_err(outi.cpu().numpy(), oracle.summate_incompr(k, z1, z2, pos, 1)) <= TOL
