@@ -31,6 +31,7 @@
 #include "../../include/gsfield.h"
 #include "gsf_kernels.cuh"
 #include "gsf_grid_kernels.cuh"
+#include "gsf_krige_kernels.cuh"
 
 namespace {
 
@@ -1095,6 +1096,8 @@ int run_host_call(Problem p, const GridSpec *grid)
     return GSF_OK;
 }
 
+#include "gsf_krige_host.inc"
+
 }  // namespace
 
 // =============================================================================================
@@ -1181,6 +1184,15 @@ int gsf_summate_on_stream(int kind, int dim, int64_t n_modes, int64_t n_points, 
     collect_stats(p, used, ms, P, L, 2, 2, 0);
     if (prev != pd) cudaSetDevice(prev);
     return GSF_OK;
+}
+
+int gsf_krige(int64_t n_cond, int64_t n_points, const double *krig_mat, int64_t mat_s0, int64_t mat_s1,
+              const double *krig_vecs, int64_t vecs_s0, int64_t vecs_s1, const double *cond, int64_t cond_s,
+              double *field, double *error, int num_threads)
+{
+    (void)num_threads;
+    KrigeProblem k{n_cond, n_points, krig_mat, mat_s0, mat_s1, krig_vecs, vecs_s0, vecs_s1, cond, cond_s, field, error};
+    return run_krige(k);
 }
 
 int gsf_summate_ex(const gsf_request *r)

@@ -86,6 +86,8 @@ def _load():
     L.gsf_summate.argtypes = head + a2 + a1 + a1 + a2 + [_vp, _int]
     L.gsf_summate_incompr.argtypes = head + a2 + a1 + a1 + a2 + [_vp, _i64, _i64, _int]
     L.gsf_summate_fourier.argtypes = head + a1 + a2 + a1 + a1 + a2 + [_vp, _int]
+    L.gsf_krige.argtypes = [_i64, _i64] + a2 + a2 + a1 + [_vp, _vp, _int]
+    L.gsf_krige.restype = _int
     L.gsf_summate_ex.argtypes = [ctypes.POINTER(GsfRequest)]
     L.gsf_set_grid_detection.argtypes = [_int]
     L.gsf_summate_on_stream.argtypes = [_int] + head + a1 + a2 + a1 + a1 + a2 + [_vp, _i64, _i64, _vp]
@@ -371,6 +373,36 @@ def summate_fourier_grid(spectrum_factor, modes, z1, z2, axes, scale=1.0, offset
 def set_grid_detection(enabled=True):
     """Automatic structured-grid detection in summate*/(host pos): True/False, None = GSF_GRID_DETECT."""
     _load().gsf_set_grid_detection(-1 if enabled is None else (1 if enabled else 0))
+
+
+# ---------------------------------------------------------------------------------------------
+# kriging (SURVEY.md 8 f4): mirrors calc_field_krige / calc_field_krige_and_variance, src/lib.rs:86-118
+
+def _krige(krige_mat, krig_vecs, cond, want_error, num_threads):
+    L = _load()
+    mat, vecs, cnd = _Arr(krige_mat, 2, "krige_mat"), _Arr(krig_vecs, 2, "krig_vecs"), _Arr(cond, 1, "cond")
+    c = mat.shape[0]
+    if mat.shape[1] != c or vecs.shape[0] != c or cnd.shape[0] != c:
+        raise ValueError("shape mismatch: krige_mat %s, krig_vecs %s, cond %s (src/krige.rs:30-32)"
+                         % (mat.shape, vecs.shape, cnd.shape))
+    m = vecs.shape[1]
+    field = np.empty(m, dtype=np.float64)
+    error = np.empty(m, dtype=np.float64) if want_error else None
+    rc = L.gsf_krige(c, m, *mat.args(), *vecs.args(), *cnd.args(), field.ctypes.data,
+                     error.ctypes.data if want_error else None, _threads(num_threads))
+    if rc:
+        _raise(rc)
+    return (field, error) if want_error else field
+
+
+def calc_field_krige(krige_mat, krig_vecs, cond, num_threads=None):
+    """Kriging field (reference: calc_field_krige_py, src/lib.rs:104-118)."""
+    return _krige(krige_mat, krig_vecs, cond, False, num_threads)
+
+
+def calc_field_krige_and_variance(krige_mat, krig_vecs, cond, num_threads=None):
+    """Kriging field and error variance (reference: calc_field_krige_and_variance_py, src/lib.rs:86-102)."""
+    return _krige(krige_mat, krig_vecs, cond, True, num_threads)
 
 
 # ---------------------------------------------------------------------------------------------

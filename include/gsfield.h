@@ -132,6 +132,19 @@ int gsf_summate_ex(const gsf_request *request);
 /* 1 / 0: enable / disable automatic structured-grid detection; -1: follow GSF_GRID_DETECT (default on). */
 int gsf_set_grid_detection(int enabled);
 
+/* ---- kriging (reference: src/krige.rs:24-118) ----------------------- */
+
+/* field[p] = sum_i cond[i] * <krig_mat[:, i], krig_vecs[:, p]>, and, if `error` is not NULL,
+ * error[p] = sum_i krig_vecs[i, p] * <krig_mat[:, i], krig_vecs[:, p]>  (the kriging variance
+ * term).  krig_mat is (n_cond, n_cond), krig_vecs (n_cond, n_points), element strides as usual;
+ * arrays may be host or device resident.  Replaces calculator_field_krige (error == NULL,
+ * src/krige.rs:93-118) and calculator_field_krige_and_variance (src/krige.rs:24-73). */
+int gsf_krige(int64_t n_cond, int64_t n_points,
+              const double *krig_mat, int64_t mat_s0, int64_t mat_s1,
+              const double *krig_vecs, int64_t vecs_s0, int64_t vecs_s1,
+              const double *cond, int64_t cond_s,
+              double *field, double *error, int num_threads);
+
 /* Host-logic introspection for tests (no device needed): the pipeline chunk sizes for n_points
  * host-resident points (returns the count, or -count if max_sizes is too small), and the exact
  * structured-grid detector (returns 1 and the axis lengths, or 0). */

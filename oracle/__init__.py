@@ -42,6 +42,8 @@ def lib():
         L.gso_summator.argtypes = common + arr2 + arr1 + arr1 + arr2 + [_dp, ctypes.c_int]
         L.gso_summator_incompr.argtypes = common + arr2 + arr1 + arr1 + arr2 + [_dp, ctypes.c_int]
         L.gso_summator_fourier.argtypes = common + arr1 + arr2 + arr1 + arr1 + arr2 + [_dp, ctypes.c_int]
+        L.gso_krige.argtypes = [_i64, _i64] + arr2 + arr2 + arr1 + [_dp, _dp, ctypes.c_int]
+        L.gso_krige.restype = ctypes.c_int
         for f in (L.gso_summator, L.gso_summator_incompr, L.gso_summator_fourier, L.gso_max_threads):
             f.restype = ctypes.c_int
         _lib = L
@@ -108,3 +110,28 @@ def summate_fourier(spectrum_factor, modes, z1, z2, pos, num_threads=None):
     if rc:
         raise ValueError("oracle summator_fourier failed rc=%d" % rc)
     return out
+
+
+def _krige(krige_mat, krig_vecs, cond, want_error, num_threads):
+    mat, vecs, cond = _a(krige_mat, 2), _a(krig_vecs, 2), _a(cond, 1)
+    c = mat.shape[0]
+    if mat.shape[1] != c or vecs.shape[0] != c or cond.shape[0] != c:
+        raise ValueError("shape mismatch (reference: assert_eq!, src/krige.rs:30-32)")
+    m = vecs.shape[1]
+    field = np.empty(m, dtype=np.float64)
+    error = np.empty(m, dtype=np.float64) if want_error else None
+    rc = lib().gso_krige(c, m, *_s(mat), *_s(vecs), *_s(cond), field.ctypes.data,
+                         error.ctypes.data if want_error else None, int(num_threads or 1))
+    if rc:
+        raise ValueError("oracle krige failed rc=%d" % rc)
+    return (field, error) if want_error else field
+
+
+def calc_field_krige(krige_mat, krig_vecs, cond, num_threads=None):
+    """reference: calc_field_krige_py, src/lib.rs:104-118 -> krige::calculator_field_krige"""
+    return _krige(krige_mat, krig_vecs, cond, False, num_threads)
+
+
+def calc_field_krige_and_variance(krige_mat, krig_vecs, cond, num_threads=None):
+    """reference: calc_field_krige_and_variance_py, src/lib.rs:86-102"""
+    return _krige(krige_mat, krig_vecs, cond, True, num_threads)

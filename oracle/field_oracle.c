@@ -221,3 +221,38 @@ int gso_max_threads(void)
     return 1;
 #endif
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* krige::calculator_field_krige[_and_variance], src/krige.rs:24-118  (SURVEY.md section 8 f4).
+ *
+ * For every target point p (column of krig_vecs):
+ *     krig_fac_i = <column i of krig_mat, column p of krig_vecs>   (:54,:111; ndarray 1-D dot on
+ *                  strided column views = sequential fold from 0.0, as for field.rs:57)
+ *     field[p] = sum_i cond_i * krig_fac_i                         (:55,:112)
+ *     error[p] = sum_i vecs[i,p] * krig_fac_i                      (:56)
+ * The reference folds over i with rayon (`into_par_iter().fold().reduce()`), so its summation
+ * order over i depends on the split; its tests allow 6 ulp (:203-226).  Here: index order.
+ * error == NULL computes the field only. */
+int gso_krige(int64_t C, int64_t M, const double *mat, int64_t ms0, int64_t ms1, const double *vecs,
+              int64_t vs0, int64_t vs1, const double *cond, int64_t cs, double *field, double *error,
+              int num_threads)
+{
+    if (C < 0 || M < 0) return GSO_ERR_DIM;
+    (void)num_threads;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(num_threads > 1 ? num_threads : 1)
+#endif
+    for (int64_t p = 0; p < M; ++p) {
+        double f = 0.0, e = 0.0;
+        for (int64_t i = 0; i < C; ++i) {
+            double fac = 0.0;
+            for (int64_t j = 0; j < C; ++j)
+                fac = fac + mat[j * ms0 + i * ms1] * vecs[j * vs0 + p * vs1];
+            f += cond[i * cs] * fac;
+            e += vecs[i * vs0 + p * vs1] * fac;
+        }
+        field[p] = f;
+        if (error) error[p] = e;
+    }
+    return GSO_OK;
+}

@@ -71,3 +71,20 @@ def test_edge_cases():
     out = oracle.summate_incompr(np.zeros((2, 1)), np.ones(1), np.ones(1), pos)
     assert np.isnan(out).all()                                             # k = 0 => 0/0, :138
     assert oracle.summate(np.ones((2, 3)), np.ones(3), np.ones(3), np.ones((2, 0))).shape == (0,)
+
+
+# ------------------------------------------------------------------------------- krige
+@pytest.fixture(scope="module")
+def krige_kat():
+    import json, os
+    from conftest import ROOT
+    raw = json.load(open(os.path.join(ROOT, "tests", "golden", "krige_rs_kat.json")))
+    return {k: np.array(v, dtype=np.float64) for k, v in raw.items() if not k.startswith("_")}
+
+
+def test_krige_golden_6ulp(krige_kat):
+    f, e = oracle.calc_field_krige_and_variance(krige_kat["krig_mat"], krige_kat["krig_vecs"], krige_kat["cond"])
+    assert _ulps_eq(f, krige_kat["field"]).all(), ulp_diff(f, krige_kat["field"])      # src/krige.rs:198-208
+    assert _ulps_eq(e, krige_kat["error"]).all(), ulp_diff(e, krige_kat["error"])      # :210-220
+    f2 = oracle.calc_field_krige(krige_kat["krig_mat"], krige_kat["krig_vecs"], krige_kat["cond"])
+    assert np.array_equal(f, f2)                                                      # :228-244
