@@ -100,3 +100,26 @@ def test_no_device_fails_loudly():
                  lambda: gc.dfma_peak(0, 1.0)):
         with pytest.raises(RuntimeError, match="no CUDA device"):
             call()
+
+
+def test_krige_surface_and_validation():
+    # src/lib.rs:86-118: calc_field_krige_and_variance / calc_field_krige (krige_mat, krig_vecs, cond, num_threads)
+    import inspect
+    for fn in (gc.calc_field_krige, gc.calc_field_krige_and_variance):
+        assert list(inspect.signature(fn).parameters) == ["krige_mat", "krig_vecs", "cond", "num_threads"]
+    mat = np.eye(3); vecs = np.ones((3, 5)); cond = np.ones(3)
+    with pytest.raises(ValueError):
+        gc.calc_field_krige(mat, vecs[:2], cond)            # src/krige.rs:31
+    with pytest.raises(ValueError):
+        gc.calc_field_krige_and_variance(mat, vecs, np.ones(4))   # :32
+    with pytest.raises(TypeError):
+        gc.calc_field_krige(mat.astype(np.float32), vecs, cond)
+    L = gc._load()
+    f = np.zeros(5)
+    assert L.gsf_krige(-1, 5, mat.ctypes.data, 3, 1, vecs.ctypes.data, 5, 1, cond.ctypes.data, 1,
+                       f.ctypes.data, None, 0) == 2          # GSF_ERR_SHAPE
+    assert L.gsf_krige(3, 5, None, 3, 1, vecs.ctypes.data, 5, 1, cond.ctypes.data, 1,
+                       f.ctypes.data, None, 0) == 6          # GSF_ERR_ARG
+    if not HAVE_GPU:
+        with pytest.raises(RuntimeError, match="no CUDA device"):
+            gc.calc_field_krige(mat, vecs, cond)
