@@ -292,6 +292,7 @@ struct Problem {
     double *out; int64_t os0, os1;
     int threads_hint = 0;
     int peer_owner = -1;                 // >= 0: device arrays live on this device, peers may read them
+    bool zero_copy = false;              // pos/out are mapped pinned host memory read over PCIe
     double scale = 1.0;                  // out = scale * sum + offset[a]   
     double offset[3] = {0.0, 0.0, 0.0};
     int nc() const { return kind == gsf::kIncompr ? dim : 1; }
@@ -339,6 +340,11 @@ void choose_variant(const DeviceCtx &d, const Problem &p, int64_t m_launch, bool
         return;
     }
     int bestP = 1, bestL = 1;
+    if (p.zero_copy && p.N < 4000) {     // see run_host_call: short tiles start the machine sooner
+        *P = 1;
+        *L = 1;
+        return;
+    }
     // a pipelined chunk is followed by the next chunk's kernel on another stream, which fills the
     // SMs as this one drains: long tiles pay off from much smaller launches
     if (m_launch >= (pipelined ? 120000 : 750000)) {
@@ -1034,8 +1040,12 @@ int run_host_call(Problem p, const GridSpec *grid)
     // Worth it only when the general kernel would take longer than the grid path's fixed cost
     // (~5 extra launches, tools/latency_sweep.py: break-even near 2e7 point*modes) and when the
     // per-axis tables stay small next to HBM.
+    // (the exact check is one long memory-bound pass: unlike the per-chunk staging copies it
+    //  does profit from many threads)
+    const int detect_threads = std::max(threads1, std::min(8, (int)std::thread::hardware_concurrency() / 2));
     if (!gs && pos_kind != 2 && p.N >= 32 && (double)p.M * (double)p.N >= 2e7 && grid_detection_enabled() &&
-        detect_grid_host(p, &detected, threads1) && detected.rows() >= 16) {
+        detect_grid_host(p, &detected, p.threads_hint > 0 ? std::min(detect_threads, p.threads_hint) : detect_threads) &&
+        detected.rows() >= 16) {
         const double table_bytes = 16.0 * (double)(p.N + 16) *
                                    ((double)detected.n[0] + (detected.dim == 3 ? (double)detected.n[1] : 0.0) +
                                     (double)detected.n_last() * p.nc());
@@ -1067,7 +1077,34 @@ int run_host_call(Problem p, const GridSpec *grid)
                 }
         }
     } else if (G == 1) {
-        rc = run_shard(*used[0], p, 0, p.M, pos_kind, out_kind, &P, &L, threads1);
+        // Zero-copy: pinned host positions and result are mapped into the device address space
+        // (UVA), so ONE full-size launch can read/write them over PCIe directly -- no chunking, no
+        // copy-engine traffic.  The algorithmic traffic is 8*(dim+nc) bytes per point against
+        // ~15 N FP64 slots, so the link is lightly used once N is large enough.
+        // The first resident wave has to wait for its own positions to cross the link, so short
+        // tiles (P = 1: ~5 MB in the first wave instead of ~12 MB) start the machine sooner unless
+        // the per-point work is long (N >= 4000).  Measured on C2: 1.02 ms vs 1.06 ms for the
+        // chunked copy pipeline (tools/e2e_probe.py).  GSF_ZERO_COPY=0 restores the pipeline.
+        static const int zero_copy = []() { const char *e = getenv("GSF_ZERO_COPY"); return e && *e ? atoi(e) : 1; }();
+        bool zc = false;
+        if (zero_copy && pos_kind == 1 && out_kind == 1 && p.ps1 == 1) {
+            void *dpos = nullptr, *dout = nullptr;
+            cudaSetDevice(used[0]->dev);
+            if (cudaHostGetDevicePointer(&dpos, const_cast<double *>(p.pos), 0) == cudaSuccess &&
+                cudaHostGetDevicePointer(&dout, p.out, 0) == cudaSuccess) {
+                Problem q = p;
+                q.pos = static_cast<const double *>(dpos);
+                q.out = static_cast<double *>(dout);
+                q.zero_copy = true;
+                rc = run_shard(*used[0], q, 0, p.M, 2, 2, &P, &L, threads1);
+                used[0]->h2d_bytes += (int64_t)p.dim * p.M * 8;
+                used[0]->d2h_bytes += (int64_t)p.nc() * p.M * 8;
+                zc = true;
+            } else {
+                cudaGetLastError();
+            }
+        }
+        if (!zc) rc = run_shard(*used[0], p, 0, p.M, pos_kind, out_kind, &P, &L, threads1);
     } else {
         std::vector<std::thread> th;
         std::vector<int> Ps(G), Ls(G);
