@@ -332,3 +332,25 @@ def test_peer_sharding_of_device_resident_data():
     gc.summate_incompr_device(dk, dz1, dz2, dpos, outi, sync=True)
     assert gc.last_stats()["n_devices"] > 1
     assert rel_err(outi.cpu().numpy(), oracle.summate_incompr(k, z1, z2, pos, 1)) <= TOL
+
+
+def test_mode_record_cache_invalidation():
+    """Identical modes skip the upload/pre-pass (records cached on the device); any change of the
+    mode arrays -- even in place, same pointers -- must be noticed."""
+    k, z1, z2, pos = _rand(71, 3, 200, 3000)
+    a1 = gc.summate(k, z1, z2, pos)
+    n1 = gc.last_stats()["kernel_launches"]
+    a2 = gc.summate(k, z1, z2, pos)
+    n2 = gc.last_stats()["kernel_launches"]
+    assert np.array_equal(a1, a2) and n2 == n1 - 1            # second call: no gsf_prep_modes launch
+    z1[17] += 0.5                                             # in-place edit, same buffer
+    b = gc.summate(k, z1, z2, pos)
+    assert gc.last_stats()["kernel_launches"] == n1
+    assert rel_err(b, oracle.summate(k, z1, z2, pos)) <= TOL and not np.array_equal(a1, b)
+    # same raw modes, other kind / scale => other records
+    c = gc.summate_incompr(k, z1, z2, pos)
+    assert rel_err(c, oracle.summate_incompr(k, z1, z2, pos)) <= TOL
+    d = gc.summate_scaled(k, z1, z2, pos, scale=3.0)
+    assert np.max(np.abs(d - 3.0 * b)) <= 1e-12 * np.std(b)
+    e = gc.summate(k, z1, z2, pos)
+    assert np.array_equal(e, b)
