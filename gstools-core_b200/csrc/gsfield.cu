@@ -499,6 +499,26 @@ void reset_call_counters(DeviceCtx &d)
     d.err.clear();
 }
 
+// On an early (error) return work may still be in flight on the pipeline streams while the caller
+// goes on to free or reuse its buffers: drain the device's streams and drop cached state.
+struct DrainOnError {
+    DeviceCtx &d;
+    bool armed = true;
+    explicit DrainOnError(DeviceCtx &dc) : d(dc) {}
+    ~DrainOnError()
+    {
+        if (!armed) return;
+        const std::string keep = g_err;
+        for (int s = 0; s < kSlots; ++s)
+            if (d.slot[s].stream) cudaStreamSynchronize(d.slot[s].stream);
+        cudaGetLastError();
+        d.rec_valid = false;
+        d.ws_used = false;
+        for (int s = 0; s < kSlots; ++s) d.slot[s].g_counter_cap = 0;   // tile tickets may be dirty: re-zero
+        g_err = keep;
+    }
+};
+
 // ---------------------------------------------------------------------------------------------
 // Persistent host worker pool for the pageable-memory staging copies (gather into / scatter out
 // of the pinned ring).  One memcpy thread moves ~10 GB/s, a PCIe 5 x16 link ~55 GB/s, so staging
@@ -687,6 +707,7 @@ int run_shard(DeviceCtx &d, const Problem &p, int64_t j_beg, int64_t j_end, int 
 {
     GSF_CUDA(cudaSetDevice(d.dev));
     reset_call_counters(d);
+    DrainOnError guard(d);
     const int nc = p.nc();
     const int64_t m_shard = j_end - j_beg;
     int rc;
@@ -818,6 +839,7 @@ int run_shard(DeviceCtx &d, const Problem &p, int64_t j_beg, int64_t j_end, int 
     }
     for (int s = 0; s < kSlots; ++s) GSF_CUDA(cudaStreamSynchronize(d.slot[s].stream));
     d.ws_used = false;   // everything that read the workspace has finished
+    guard.armed = false;
     return GSF_OK;
 }
 
