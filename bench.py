@@ -120,12 +120,21 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
+def host_threads():
+    """All host cores this process may use.  (torchrun exports OMP_NUM_THREADS=1 to its workers, so
+    omp_get_max_threads() would under-report; the oracle takes the thread count explicitly.)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_reference_rate(w, seconds, threads=None):
     """Oracle (C restatement of the Rayon path) on a bounded point sample; returns (Gpm/s, info)."""
     import oracle
     from gstools_core import workloads
 
-    threads = threads or oracle.max_threads()
+    threads = threads or host_threads()
     fn = getattr(oracle, w["kind"])
     n, m = w["n"], w["m"]
     # probe to size the sample
@@ -154,7 +163,7 @@ def run_reference(args):
     from gstools_core import workloads
 
     w = workloads.make(args.workload, args.scale)
-    threads = oracle.max_threads()
+    threads = host_threads()
     steps = max(1, args.steps)
     warm = max(0, args.warmup)
     # bounded sample per step: the whole run (warm-up + K steps) is sized to ~2 minutes of CPU time
