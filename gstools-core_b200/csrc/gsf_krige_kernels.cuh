@@ -9,13 +9,13 @@
 // * field only: field = (K c)^T V -- O(C^2 + C M) instead of the reference's O(C^2 M): one small
 //   mat-vec (gsf_krige_matvec) and one HBM-bound pass over V (gsf_krige_gemv).
 // * with variance: Y = K^T V is an FP64 GEMM (2 C^2 M flops) that is never stored: each CTA owns 64
-//   points, walks the condition rows in blocks of 32 with DMMA.8x8x4 accumulators, and folds every
-//   finished 32 x 64 block of Y into the two running column sums (x c_i, x V[i,p]) in registers.
+//   points, walks the condition rows in blocks of 64 (two 8-row DMMA tiles per warp, so every B
+//   fragment feeds two DMMA.8x8x4) and folds every finished 64 x 64 block of Y into the two running column sums (x c_i, x V[i,p]) in registers.
 //   Operand tiles go through a 2-stage cp.async ring; row strides 36 / 68 doubles (4 mod 16) make
 //   the "4 k-rows x 8 consecutive" fragment loads bank-conflict free (see gsf_grid_kernels.cuh).
 //   Few points => the condition rows are split over gridDim.y; partial sums are combined in split
 //   order by gsf_krige_reduce (deterministic).
-// Inputs are zero-padded device copies: Cp = roundup(C, 32), Mp = roundup(M, 64).
+// Inputs are zero-padded device copies: Cp = roundup(C, 64), Mp = roundup(M, 64).
 #pragma once
 
 #include <cuda_runtime.h>
@@ -27,7 +27,8 @@ namespace gsf {
 
 constexpr int kKrigeThreads = 128;
 constexpr int kKrigeBP = 64;      // points per CTA
-constexpr int kKrigeBI = 32;      // condition rows per block (8 per warp)
+constexpr int kKrigeRT = 1;       // 8-row DMMA tiles per warp (2 was measured: 255 regs + spills, no net gain)
+constexpr int kKrigeBI = 32 * kKrigeRT;   // condition rows per block
 constexpr int kKrigeBK = 32;      // contraction block
 constexpr int kKrigeSA = kKrigeBI + 4;   // smem row stride of the K tile (doubles)
 constexpr int kKrigeSB = kKrigeBP + 4;   // smem row stride of the V tile
@@ -67,11 +68,12 @@ __global__ void __launch_bounds__(kKrigeThreads) gsf_krige_gemm(KrigeArgs a)
         const int64_t j0 = kb * kKrigeBK;
         double *dA = sA + st * kKrigeBK * kKrigeSA;
         double *dB = sB + st * kKrigeBK * kKrigeSB;
-        // K tile: 32 rows (j) x 32 doubles (i) = 512 x 16 B, 4 per thread
+        // K tile: 32 rows (j) x BI doubles (i) in 16 B units, 4*RT per thread
+        constexpr int kUnitsPerRow = kKrigeBI / 2;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int e = tid + q * kKrigeThreads;         // 0..511
-            const int r = e >> 4, c2 = e & 15;
+        for (int q = 0; q < 4 * kKrigeRT; ++q) {
+            const int e = tid + q * kKrigeThreads;
+            const int r = e / kUnitsPerRow, c2 = e % kUnitsPerRow;
             cp_async16(dA + r * kKrigeSA + 2 * c2, a.mat + (j0 + r) * a.cp + i0 + 2 * c2);
         }
         // V tile: 32 rows (j) x 64 doubles (p) = 1024 x 16 B, 8 per thread
@@ -90,41 +92,51 @@ __global__ void __launch_bounds__(kKrigeThreads) gsf_krige_gemm(KrigeArgs a)
 
     for (int64_t ib = ib0; ib < ib1; ++ib) {
         const int64_t i0 = ib * kKrigeBI;
-        double acc[8][2];
+        double acc[kKrigeRT][8][2];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) acc[t][0] = acc[t][1] = 0.0;
+        for (int rt = 0; rt < kKrigeRT; ++rt)
+#pragma unroll
+            for (int t = 0; t < 8; ++t) acc[rt][t][0] = acc[rt][t][1] = 0.0;
 
+        // 2-stage ring, ONE barrier per K block: the barrier at the top both publishes block kb
+        // (after this thread's cp.async group landed) and guarantees everybody finished reading
+        // the other stage (block kb-1), which the loads for kb+1 then overwrite during the DMMAs.
         load_tiles(0, i0, 0);
         for (int64_t kb = 0; kb < n_kblocks; ++kb) {
             const int st = (int)(kb & 1);
-            if (kb + 1 < n_kblocks) {
-                load_tiles(st ^ 1, i0, kb + 1);
-                cp_async_wait<1>();
-            } else {
-                cp_async_wait<0>();
-            }
+            cp_async_wait<0>();
             __syncthreads();
-            const double *fa = sA + st * kKrigeBK * kKrigeSA + (lane & 3) * kKrigeSA + warp * 8 + (lane >> 2);
+            if (kb + 1 < n_kblocks) load_tiles(st ^ 1, i0, kb + 1);
+            const double *fa = sA + st * kKrigeBK * kKrigeSA + (lane & 3) * kKrigeSA + warp * 8 * kKrigeRT + (lane >> 2);
             const double *fb = sB + st * kKrigeBK * kKrigeSB + (lane & 3) * kKrigeSB + (lane >> 2);
 #pragma unroll
             for (int k4 = 0; k4 < kKrigeBK / 4; ++k4) {
-                const double af = fa[4 * k4 * kKrigeSA];
+                double af[kKrigeRT];
 #pragma unroll
-                for (int t = 0; t < 8; ++t) dmma884(acc[t][0], acc[t][1], af, fb[4 * k4 * kKrigeSB + 8 * t]);
+                for (int rt = 0; rt < kKrigeRT; ++rt) af[rt] = fa[4 * k4 * kKrigeSA + 8 * rt];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const double bf = fb[4 * k4 * kKrigeSB + 8 * t];
+#pragma unroll
+                    for (int rt = 0; rt < kKrigeRT; ++rt) dmma884(acc[rt][t][0], acc[rt][t][1], af[rt], bf);
+                }
             }
-            __syncthreads();
         }
+        __syncthreads();   // all reads of the last stages done before the next row block reloads them
         // fold this block of Y into the running column sums
-        const int64_t i = i0 + warp * 8 + (lane >> 2);
-        const double ci = a.cond[i];
-        const double2 *vrow = reinterpret_cast<const double2 *>(a.vecs + i * a.ldv + p0);
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-            const double2 v = __ldg(vrow + 4 * t + (lane & 3));
-            fld[t][0] = fma(ci, acc[t][0], fld[t][0]);
-            fld[t][1] = fma(ci, acc[t][1], fld[t][1]);
-            err[t][0] = fma(v.x, acc[t][0], err[t][0]);
-            err[t][1] = fma(v.y, acc[t][1], err[t][1]);
+        for (int rt = 0; rt < kKrigeRT; ++rt) {
+            const int64_t i = i0 + warp * 8 * kKrigeRT + 8 * rt + (lane >> 2);
+            const double ci = a.cond[i];
+            const double2 *vrow = reinterpret_cast<const double2 *>(a.vecs + i * a.ldv + p0);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const double2 v = __ldg(vrow + 4 * t + (lane & 3));
+                fld[t][0] = fma(ci, acc[rt][t][0], fld[t][0]);
+                fld[t][1] = fma(ci, acc[rt][t][1], fld[t][1]);
+                err[t][0] = fma(v.x, acc[rt][t][0], err[t][0]);
+                err[t][1] = fma(v.y, acc[rt][t][1], err[t][1]);
+            }
         }
     }
 
