@@ -9,13 +9,13 @@
 // * field only: field = (K c)^T V -- O(C^2 + C M) instead of the reference's O(C^2 M): one small
 //   mat-vec (gsf_krige_matvec) and one HBM-bound pass over V (gsf_krige_gemv).
 // * with variance: Y = K^T V is an FP64 GEMM (2 C^2 M flops) that is never stored: each CTA owns 64
-//   points, walks the condition rows in blocks of 64 (two 8-row DMMA tiles per warp, so every B
-//   fragment feeds two DMMA.8x8x4) and folds every finished 64 x 64 block of Y into the two running column sums (x c_i, x V[i,p]) in registers.
+//   points, walks the condition rows in blocks of 32*RT with DMMA.8x8x4 accumulators and folds every
+//   finished block of Y into the two running column sums (x c_i, x V[i,p]) in registers.
 //   Operand tiles go through a 2-stage cp.async ring; row strides 36 / 68 doubles (4 mod 16) make
 //   the "4 k-rows x 8 consecutive" fragment loads bank-conflict free (see gsf_grid_kernels.cuh).
 //   Few points => the condition rows are split over gridDim.y; partial sums are combined in split
 //   order by gsf_krige_reduce (deterministic).
-// Inputs are zero-padded device copies: Cp = roundup(C, 64), Mp = roundup(M, 64).
+// Inputs are zero-padded device copies: Cp = roundup(C, 32*RT), Mp = roundup(M, 64).
 #pragma once
 
 #include <cuda_runtime.h>
