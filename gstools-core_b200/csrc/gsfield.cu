@@ -549,7 +549,7 @@ class HostPool {
             total_ = n_parts;
             next_.store(0);
             done_.store(0);
-            ++gen_;
+            gen_.fetch_add(1, std::memory_order_release);
         }
         cv_work_.notify_all();
         drain();
@@ -575,12 +575,22 @@ class HostPool {
     {
         uint64_t seen = 0;
         for (;;) {
-            {
-                std::unique_lock<std::mutex> l(mu_);
-                cv_work_.wait(l, [&]() { return stop_ || gen_ != seen; });
-                if (stop_) return;
-                seen = gen_;
+            // stay hot for ~100 us after a job: calls arrive back to back, and a condition-variable
+            // wake-up costs tens of microseconds on a virtualised host
+            bool got = false;
+            const auto t_end = std::chrono::steady_clock::now() + std::chrono::microseconds(100);
+            while (std::chrono::steady_clock::now() < t_end) {
+                if (gen_.load(std::memory_order_acquire) != seen || stop_) { got = true; break; }
+#if defined(__x86_64__)
+                __builtin_ia32_pause();
+#endif
             }
+            if (!got) {
+                std::unique_lock<std::mutex> l(mu_);
+                cv_work_.wait(l, [&]() { return stop_ || gen_.load() != seen; });
+            }
+            if (stop_) return;
+            seen = gen_.load(std::memory_order_acquire);
             drain();
         }
     }
@@ -590,8 +600,8 @@ class HostPool {
     const std::function<void(int)> *job_ = nullptr;
     int total_ = 0;
     std::atomic<int> next_{0}, done_{0};
-    uint64_t gen_ = 0;
-    bool stop_ = false;
+    std::atomic<uint64_t> gen_{0};
+    std::atomic<bool> stop_{false};
 };
 
 HostPool &host_pool()
