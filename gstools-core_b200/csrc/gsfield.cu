@@ -1051,7 +1051,6 @@ int run_host_call(Problem p, const GridSpec *grid)
     std::vector<int> devs = c.devices_explicit ? c.devices : default_devices();
     for (int id : devs)
         if (id < 0 || id >= ndev_visible) return fail(GSF_ERR_ARG, "configured device %d not visible (%d devices)", id, ndev_visible);
-    bool peer_shards = false;
     if (pos_kind == 2 || out_kind == 2) {
         // device-resident data: the work runs where the data lives ...
         const int dv = pos_kind == 2 ? pos_dev : out_dev;
@@ -1069,8 +1068,7 @@ int run_host_call(Problem p, const GridSpec *grid)
             for (int id : devs) ok = ok && enable_peer(id, dv);
         }
         if (ok) {
-            peer_shards = true;
-            p.peer_owner = dv;
+            p.peer_owner = dv;   // peers may read the owner's arrays
         } else {
             devs.assign(1, dv);
         }
