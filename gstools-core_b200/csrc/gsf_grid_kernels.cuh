@@ -334,32 +334,65 @@ __global__ void __launch_bounds__(256) gsf_dmma_peak_kernel(double *sink, int it
 }
 
 // ------------------------------------------------------------------------------------------
-// Exact test "is pos a C-order flattened rectilinear grid?" for device-resident positions:
-// every point must equal (axis0[j0], axis1[j1], axis2[j2]) bit for bit, where the candidate axes
-// are read from pos itself (first occurrence along each axis).  flag[0] is set to 1 on mismatch.
+// Structured-grid detection for DEVICE-resident positions (the host-resident case is handled by
+// detect_grid_host on the CPU).  Same logic: candidate axis lengths from the first index at which
+// each slower coordinate changes, then an exact bitwise verification of every point.
+
+// first[a] = min { j : pos[a, j] != pos[a, 0] bitwise }  (left at n_points if the row is constant)
+__global__ void gsf_grid_first_change(const double *pos, int64_t ps0, int64_t ps1, int n_rows, int64_t n_points,
+                                      unsigned long long *first)
+{
+    const int a = blockIdx.y;
+    if (a >= n_rows) return;
+    const double *row = pos + a * ps0;
+    const long long b0 = __double_as_longlong(row[0]);
+    unsigned long long best = (unsigned long long)n_points;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_points; j += (int64_t)gridDim.x * blockDim.x)
+        if (__double_as_longlong(row[j * ps1]) != b0) { best = (unsigned long long)j; break; }
+    // one global atomic per CTA: warp butterfly, then shared memory (a same-address atomic per thread
+    // would serialise ~1e6 operations in L2)
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = other < best ? other : best;
+    }
+    __shared__ unsigned long long s_best;
+    if (threadIdx.x == 0) s_best = (unsigned long long)n_points;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0 && best < (unsigned long long)n_points) atomicMin(&s_best, best);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_best < (unsigned long long)n_points) atomicMin(first + a, s_best);
+}
+
 struct GridCheckArgs {
     const double *pos; int64_t ps0, ps1;
     int dim;
     int64_t n[3];
     int64_t n_points;
-    int *flag;
+    int *flag;                  // set to 1 on any mismatch
+    double *axes;               // out: the axis vectors, concatenated (axis 0, 1, 2)
 };
 
+// every point must equal (axis0[j0], axis1[j1], axis2[j2]) bit for bit, where axis a is read from
+// pos itself (points whose other indices are 0); also writes the axis vectors to `axes`
 __global__ void gsf_grid_check(GridCheckArgs a)
 {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= a.n_points) return;
-    int64_t idx[3], rem = j;
+    int64_t idx[3] = {0, 0, 0}, rem = j;
     for (int d = a.dim - 1; d >= 0; --d) {
         idx[d] = rem % a.n[d];
         rem /= a.n[d];
     }
-    int64_t stride = 1;
+    int64_t stride = 1, axis_off = 0;
+    for (int d = 0; d < a.dim; ++d) axis_off += a.n[d];
     bool bad = false;
     for (int d = a.dim - 1; d >= 0; --d) {
-        const double want = a.pos[d * a.ps0 + (idx[d] * stride) * a.ps1];   // axis value: others at 0
+        axis_off -= a.n[d];
+        const double want = a.pos[d * a.ps0 + (idx[d] * stride) * a.ps1];   // axis value: other indices 0
         const double have = a.pos[d * a.ps0 + j * a.ps1];
         bad |= __double_as_longlong(want) != __double_as_longlong(have);
+        if (j == idx[d] * stride) a.axes[axis_off + idx[d]] = have;         // this point defines axis d
         stride *= a.n[d];
     }
     if (bad) atomicExch(a.flag, 1);

@@ -138,6 +138,8 @@ struct DeviceCtx {
     bool rec_valid = false;
     double *g_axes = nullptr, *g_E0 = nullptr, *g_E1 = nullptr, *g_F = nullptr;   // grid-path tables
     size_t g_axes_cap = 0, g_E0_cap = 0, g_E1_cap = 0, g_F_cap = 0;
+    double *g_counter0 = nullptr;        // scratch of the device-side grid detection
+    size_t g_counter0_cap = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof;   // pool of timing events
     size_t prof_used = 0;
     cudaEvent_t prep_beg = nullptr, prep_end = nullptr;
@@ -254,6 +256,7 @@ void free_device_ctx(DeviceCtx *d)
         if (d->g_E0) cudaFree(d->g_E0);
         if (d->g_E1) cudaFree(d->g_E1);
         if (d->g_F) cudaFree(d->g_F);
+        if (d->g_counter0) cudaFree(d->g_counter0);
         for (auto &pr : d->prof) {
             cudaEventDestroy(pr.first);
             cudaEventDestroy(pr.second);
@@ -1101,11 +1104,28 @@ int run_host_call(Problem p, const GridSpec *grid)
         if (table_bytes <= 8e9) gs = &detected;
     }
 
+    // device-resident positions and result (synchronous API): detect on the device
+    bool axes_on_device = false;
+    if (!gs && pos_kind == 2 && out_kind == 2 && G == 1 && p.peer_owner < 0 && p.N >= 32 &&
+        (double)p.M * (double)p.N >= 2e7 && grid_detection_enabled()) {
+        bool found = false;
+        if ((rc = detect_grid_device(*used[0], p, &detected, &found))) return rc;
+        if (found) {
+            const double table_bytes = 16.0 * (double)(p.N + 16) *
+                                       ((double)detected.n[0] + (detected.dim == 3 ? (double)detected.n[1] : 0.0) +
+                                        (double)detected.n_last() * p.nc());
+            if (table_bytes <= 8e9) {
+                gs = &detected;
+                axes_on_device = true;
+            }
+        }
+    }
+
     int P = 0, L = 0;
     if (gs) {
         const int64_t R = gs->rows();
         if (G == 1) {
-            rc = run_grid(*used[0], p, *gs, 0, R, out_kind, threads1);
+            rc = run_grid(*used[0], p, *gs, 0, R, out_kind, threads1, axes_on_device);
         } else {
             std::vector<std::thread> th;
             for (int g = 0; g < G; ++g) {

@@ -194,3 +194,44 @@ def test_baseline_configs_grid_vs_general(cfg):
         gen = fn(*w["args"])
         assert gc.last_stats()["grid_path"] == 0
         assert rel_err(got, gen) <= TOL
+
+
+def test_device_resident_grid_detection():
+    """Synchronous API with device-resident pos/out: the grid is detected ON the device (two small
+    kernels) and routed to the GEMM path; the stream-ordered API never detects (it must not sync)."""
+    torch = pytest.importorskip("torch")
+    axes = [np.linspace(0, 50, 41), np.linspace(-5, 5, 37), np.linspace(2, 9, 64)]
+    pos = expand(axes)
+    k, z1, z2, sf = modes(12, 3, 300, heavy=True)
+    ref = oracle.summate(k, z1, z2, pos, oracle.max_threads())
+    dpos = torch.from_numpy(pos).cuda()
+    out = torch.empty(pos.shape[1], dtype=torch.float64, device="cuda")
+    gc.set_grid_detection(True)
+    gc.summate_device(k, z1, z2, dpos, out, sync=True)
+    assert gc.last_stats()["grid_path"] == 1
+    assert rel_err(out.cpu().numpy(), ref) <= TOL
+    # incompressible, F-ordered device output
+    outi = torch.empty((pos.shape[1], 3), dtype=torch.float64, device="cuda").t()
+    gc.summate_incompr_device(k, z1, z2, dpos, outi, sync=True)
+    assert gc.last_stats()["grid_path"] == 1
+    assert rel_err(outi.cpu().numpy(), oracle.summate_incompr(k, z1, z2, pos)) <= TOL
+    # a perturbed point => general kernel
+    q = pos.copy(); q[1, 4321] += 1e-9
+    dq = torch.from_numpy(q).cuda()
+    gc.summate_device(k, z1, z2, dq, out, sync=True)
+    assert gc.last_stats()["grid_path"] == 0
+    assert rel_err(out.cpu().numpy(), oracle.summate(k, z1, z2, q, oracle.max_threads())) <= TOL
+    # 2-D grid with AoS (Fortran-ordered) device positions: strides handled on the device
+    ax2 = [np.linspace(0, 3, 300), np.linspace(0, 2, 200)]
+    p2 = expand(ax2)
+    k2, a, b, _ = modes(13, 2, 400)
+    d2 = torch.from_numpy(np.ascontiguousarray(p2.T)).cuda().t()
+    o2 = torch.empty(p2.shape[1], dtype=torch.float64, device="cuda")
+    gc.summate_device(k2, a, b, d2, o2, sync=True)
+    assert gc.last_stats()["grid_path"] == 1
+    assert rel_err(o2.cpu().numpy(), oracle.summate(k2, a, b, p2, oracle.max_threads())) <= TOL
+    # stream-ordered call: no detection
+    gc.summate_device(k, z1, z2, dpos, out, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert gc.last_stats()["grid_path"] == 0
+    assert rel_err(out.cpu().numpy(), ref) <= TOL
