@@ -30,6 +30,10 @@
 namespace gsf {
 
 constexpr int kThreads = 128;     // threads per CTA
+#ifndef GSF_TAIL_P
+#define GSF_TAIL_P 1
+#endif
+constexpr int kTailP = GSF_TAIL_P;  // points per thread of the short tiles that end a launch
 constexpr int kModeBlock = 256;   // mode records per shared-memory stage
 constexpr int kStages = 2;
 constexpr double kMagic = 6755399441055744.0;  // 1.5 * 2^52
@@ -376,10 +380,11 @@ __global__ void __launch_bounds__(kThreads) gsf_sum_kernel(SumArgs a)
 #ifdef GSF_NO_HYBRID_TAIL
     sum_tile<D, NC, P, L>(a, b * kTile, s_rec, s_bar);
 #else
-    if (P == 1 || L > 1 || b < a.n_big) {
+    if (P <= kTailP || L > 1 || b < a.n_big) {
         sum_tile<D, NC, P, L>(a, b * kTile, s_rec, s_bar);
     } else {
-        sum_tile<D, NC, 1, (P == 1 ? L : 1)>(a, a.n_big * kTile + (b - a.n_big) * kThreads, s_rec, s_bar);
+        sum_tile<D, NC, kTailP, (P <= kTailP ? L : 1)>(a, a.n_big * kTile + (b - a.n_big) * (kThreads * kTailP), s_rec,
+                                                       s_bar);
     }
 #endif
 }

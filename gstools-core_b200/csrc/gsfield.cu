@@ -388,7 +388,7 @@ int launch_sum(DeviceCtx &d, const Problem &p, const double *kpos, int64_t ps0, 
     // `tail` resident waves so that the machine drains in small steps (see gsf_sum_kernel)
     const int64_t tile = (int64_t)P * (kThreads / L);
     int64_t n_big = (m + tile - 1) / tile, n_small = 0;
-    if (P > 1 && L == 1) {
+    if (P > gsf::kTailP && L == 1) {
         static const double tail_waves = []() {
             const char *e = getenv("GSF_TAIL_WAVES");
             return e && *e ? atof(e) : 0.5;
@@ -397,7 +397,8 @@ int launch_sum(DeviceCtx &d, const Problem &p, const double *kpos, int64_t ps0, 
         int64_t tail_pts = (int64_t)(tail_waves * (double)resident * (double)tile);
         tail_pts = std::min(tail_pts, m);
         n_big = (m - tail_pts) / tile;
-        n_small = (m - n_big * tile + kThreads - 1) / kThreads;
+        const int64_t small_tile = (int64_t)kThreads * gsf::kTailP;
+        n_small = (m - n_big * tile + small_tile - 1) / small_tile;
     }
     a.n_big = n_big;
     const int64_t grid = n_big + n_small;
