@@ -5,8 +5,12 @@ import pytest
 import gstools_core as gc
 import oracle
 
+import os
+
 pytestmark = pytest.mark.gpu
 TOL = 1e-9
+N_GENERAL = int(os.environ.get("GSF_FUZZ_GENERAL", "40"))     # raise for a soak run
+N_GRID = int(os.environ.get("GSF_FUZZ_GRID", "20"))
 
 
 def rel_err(got, ref):
@@ -34,7 +38,7 @@ def strided(rng, a):
     return big[sl]
 
 
-@pytest.mark.parametrize("seed", range(40))
+@pytest.mark.parametrize("seed", range(N_GENERAL))
 def test_fuzz_general(seed):
     if gc.device_count() < 1:
         pytest.fail("no CUDA device")
@@ -67,7 +71,7 @@ def test_fuzz_general(seed):
     assert rel_err(got, ref) <= TOL, (kind, d, n, m)
 
 
-@pytest.mark.parametrize("seed", range(20))
+@pytest.mark.parametrize("seed", range(N_GRID))
 def test_fuzz_grid(seed):
     rng = np.random.default_rng(2000 + seed)
     kind = ["summate", "summate_incompr", "summate_fourier"][seed % 3]
