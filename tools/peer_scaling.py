@@ -5,6 +5,7 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, "gstools-core_b200")]
 import numpy as np, torch, gstools_core as gc
 from gstools_core import workloads
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 0.1
+gc.set_grid_detection(False)   # measure the general kernel (a detected grid would run the GEMM path on the owner GPU)
 w = workloads.make("c5", scale)
 k, z1, z2, pos = w["args"]; pm = w["m"] * w["n"]
 dpos = torch.from_numpy(pos).cuda(0); out = torch.empty(w["m"], dtype=torch.float64, device="cuda:0")
