@@ -337,6 +337,7 @@ def test_peer_sharding_of_device_resident_data():
 def test_mode_record_cache_invalidation():
     """Identical modes skip the upload/pre-pass (records cached on the device); any change of the
     mode arrays -- even in place, same pointers -- must be noticed."""
+    gc.shutdown()                                             # drop any cached records
     k, z1, z2, pos = _rand(71, 3, 200, 3000)
     a1 = gc.summate(k, z1, z2, pos)
     n1 = gc.last_stats()["kernel_launches"]
