@@ -265,7 +265,7 @@ def run_ours(args):
     gc.set_grid_detection(False)
     gc.set_profiling(False)
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and os.environ.get("GSF_BENCH_NO_SAMPLER") != "1":
         sampler.start()
         time.sleep(0.4)          # let nvidia-smi come up so that it samples the timed region
     for i in range(W):
@@ -304,16 +304,23 @@ def run_ours(args):
     for i in range(W):
         host_fn(*margs, pin_np[i % 2])
     barrier()
+    # K host-synchronous calls, repeated three times; the MEDIAN repetition is reported (all three
+    # are listed): this loop runs on the host's clock and a noisy neighbour on the shared box moves
+    # a single repetition by +-10 %.
     e2e_launches = 0
-    t0 = time.perf_counter()
-    for i in range(K):
-        res = host_fn(*margs, pin_np[i % 2])
-        e2e_launches += gc.last_stats()["kernel_launches"]
-    torch.cuda.synchronize()
-    e2e_local = (time.perf_counter() - t0) * 1e3
+    reps = []
+    for rep in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(K):
+            res = host_fn(*margs, pin_np[i % 2])
+            e2e_launches += gc.last_stats()["kernel_launches"]
+        torch.cuda.synchronize()
+        e2e_local = (time.perf_counter() - t0) * 1e3
+        barrier()
+        reps.append(max_over_ranks(e2e_local) / K)
     st = gc.last_stats()
-    barrier()
-    e2e_ms = max_over_ranks(e2e_local) / K
+    e2e_ms = sorted(reps)[1]
     checksum = float(res.sum())
 
     # ---- same call from PAGEABLE host memory (plain numpy arrays, what GSTools passes today):
@@ -415,6 +422,7 @@ def run_ours(args):
                 "h2d_bytes_per_step": st["h2d_bytes"], "d2h_bytes_per_step": st["d2h_bytes"],
                 "api": "gstools_core.%s(host arrays; pos pinned, result in a host ndarray)" % kind,
                 "chunks_per_step": st["n_chunks"], "checksum": checksum,
+                "repetitions_ms_per_step": reps, "reported": "median of 3 repetitions of K steps",
                 "pageable_input": {"value": world * pm / (e2e_pageable_ms * 1e-3) / 1e9, "unit": UNIT,
                                    "ms_per_step": e2e_pageable_ms, "steps": Kp,
                                    "note": "same call on plain (pageable) numpy positions"}},
