@@ -423,6 +423,9 @@ def run_ours(args):
                 "api": "gstools_core.%s(host arrays; pos pinned, result in a host ndarray)" % kind,
                 "chunks_per_step": st["n_chunks"], "checksum": checksum,
                 "repetitions_ms_per_step": reps, "reported": "median of 3 repetitions of K steps",
+                "transfer": ("zero-copy: one launch reads the pinned positions and writes the pinned result over "
+                             "PCIe inside the timed call (no separate cudaMemcpy)" if st["n_chunks"] == 1 and
+                             os.environ.get("GSF_ZERO_COPY", "1") != "0" else "chunked H2D / kernel / D2H pipeline"),
                 "pageable_input": {"value": world * pm / (e2e_pageable_ms * 1e-3) / 1e9, "unit": UNIT,
                                    "ms_per_step": e2e_pageable_ms, "steps": Kp,
                                    "note": "same call on plain (pageable) numpy positions"}},
