@@ -406,6 +406,27 @@ def calc_field_krige_and_variance(krige_mat, krig_vecs, cond, num_threads=None):
 
 
 # ---------------------------------------------------------------------------------------------
+# OUT OF SCOPE: the variogram estimators of the reference module (src/lib.rs:120-216).  The names
+# exist only so that `from gstools_core import variogram_structured, ...` in GSTools keeps
+# importing when this module stands in for the Rust wheel; calling them fails loudly.
+
+def _out_of_scope(name, where):
+    def f(*args, **kwargs):
+        raise NotImplementedError(
+            "gstools_core (B200) does not provide %s (%s): variogram estimation is out of scope of "
+            "this build (DESIGN.md section 1); use GSTools' Cython backend for it." % (name, where))
+    f.__name__ = name
+    f.__doc__ = "Not provided by the B200 build (reference: %s)." % where
+    return f
+
+
+variogram_structured = _out_of_scope("variogram_structured", "src/lib.rs:120-131")
+variogram_ma_structured = _out_of_scope("variogram_ma_structured", "src/lib.rs:133-147")
+variogram_directional = _out_of_scope("variogram_directional", "src/lib.rs:149-186")
+variogram_unstructured = _out_of_scope("variogram_unstructured", "src/lib.rs:188-216")
+
+
+# ---------------------------------------------------------------------------------------------
 # device-resident, stream-ordered entry points
 
 def _on_stream(kind, sf, cov_samples, z1, z2, pos, out, stream, sync=False):

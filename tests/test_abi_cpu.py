@@ -123,3 +123,10 @@ def test_krige_surface_and_validation():
     if not HAVE_GPU:
         with pytest.raises(RuntimeError, match="no CUDA device"):
             gc.calc_field_krige(mat, vecs, cond)
+
+
+def test_variogram_names_fail_loudly():
+    # out of scope: importable for GSTools, but never a silent fallback
+    for name in ("variogram_structured", "variogram_ma_structured", "variogram_directional", "variogram_unstructured"):
+        with pytest.raises(NotImplementedError, match="out of scope"):
+            getattr(gc, name)(np.ones((3, 3)))
