@@ -29,12 +29,18 @@
 
 namespace gsf {
 
-constexpr int kThreads = 128;     // threads per CTA
+#ifndef GSF_THREADS
+#define GSF_THREADS 128
+#endif
+#ifndef GSF_MODE_BLOCK
+#define GSF_MODE_BLOCK 256
+#endif
+constexpr int kThreads = GSF_THREADS;   // threads per CTA (128: measured best of 64/128/256, tools/micro/tune_sum.cu)
 #ifndef GSF_TAIL_P
 #define GSF_TAIL_P 1
 #endif
 constexpr int kTailP = GSF_TAIL_P;  // points per thread of the short tiles that end a launch
-constexpr int kModeBlock = 256;   // mode records per shared-memory stage
+constexpr int kModeBlock = GSF_MODE_BLOCK;   // mode records per shared-memory stage
 constexpr int kStages = 2;
 constexpr double kMagic = 6755399441055744.0;  // 1.5 * 2^52
 
