@@ -28,6 +28,9 @@
 
 namespace gsf {
 
+#ifndef GSF_GRID_MIN_CTAS
+#define GSF_GRID_MIN_CTAS 1
+#endif
 constexpr int kGridThreads = 128;   // 4 warps
 constexpr int kGridRows = 32;       // rows per CTA (8 per warp)
 constexpr int kGridBK = 16;         // modes per K block (32 contraction steps)
@@ -122,7 +125,7 @@ struct GridGemmArgs {
 };
 
 template <int D, int NT>
-__global__ void __launch_bounds__(kGridThreads) gsf_grid_gemm(GridGemmArgs a)
+__global__ void __launch_bounds__(kGridThreads, GSF_GRID_MIN_CTAS) gsf_grid_gemm(GridGemmArgs a)
 {
     constexpr int BN = 8 * NT;
     constexpr int BNP = grid_bnp(NT);
