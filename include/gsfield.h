@@ -185,7 +185,10 @@ int gsf_host_free(void *ptr);
 int gsf_shard_bounds(int64_t n_points, int n_shards, int shard, int64_t *begin, int64_t *end);
 /* Points per pipeline chunk for host-resident data (0 = default). */
 int gsf_set_chunk_points(int64_t chunk_points);
-/* Force the kernel variant (0,0 = heuristic).  P in {1,2,4}, L in {1,2,4,8,16,32}. */
+/* Force the kernel variant (0,0 = heuristic): P points per thread, L lanes sharing one point's
+ * modes.  Built for dim <= 3: (P, 1) with P in {1,2,3,4}, and (1 or 2, L) with L in
+ * {2,4,8,16,32}; for dim 4..8: (1,1), (1,4), (1,32).  Anything else returns GSF_ERR_ARG (checked
+ * against the dim-3 table here; a forced pair a later call's dim lacks falls back to the heuristic). */
 int gsf_set_variant(int points_per_thread, int lanes_per_point);
 /* Enable CUDA-event timing of the kernels (fills kernel_ms / prep_ms; adds event-sync overhead
  * only in gsf_get_last_stats). */
