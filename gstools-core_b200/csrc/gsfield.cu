@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -32,6 +33,7 @@
 #include "gsf_kernels.cuh"
 #include "gsf_grid_kernels.cuh"
 #include "gsf_krige_kernels.cuh"
+#include "gsf_variogram_kernels.cuh"
 
 namespace {
 
@@ -1240,6 +1242,7 @@ int run_host_call(Problem p, const GridSpec *grid)
 }
 
 #include "gsf_krige_host.inc"
+#include "gsf_variogram_host.inc"
 
 }  // namespace
 
@@ -1336,6 +1339,60 @@ int gsf_krige(int64_t n_cond, int64_t n_points, const double *krig_mat, int64_t 
     (void)num_threads;
     KrigeProblem k{n_cond, n_points, krig_mat, mat_s0, mat_s1, krig_vecs, vecs_s0, vecs_s1, cond, cond_s, field, error};
     return run_krige(k);
+}
+
+int gsf_variogram_structured(int64_t n0, int64_t n1, const double *f, int64_t f_s0, int64_t f_s1,
+                             const uint8_t *mask, int64_t mask_s0, int64_t mask_s1, char estimator_type,
+                             double *variogram, int num_threads)
+{
+    (void)num_threads;
+    VarioStructProblem v{n0, n1, f, f_s0, f_s1, mask, mask_s0, mask_s1, estimator_type == 'c', variogram};
+    return run_variogram_struct(v);
+}
+
+int gsf_variogram_unstructured(int dim, int64_t n_fields, int64_t n_points, int64_t n_bins, const double *f,
+                               int64_t f_s0, int64_t f_s1, const double *bin_edges, int64_t edges_s,
+                               const double *pos, int64_t pos_s0, int64_t pos_s1, char estimator_type,
+                               char distance_type, double *variogram, uint64_t *counts, int num_threads)
+{
+    (void)num_threads;
+    VarioProblem v{};
+    v.mode = distance_type == 'e' ? gsf::kVarEuclid : gsf::kVarHaversine;   // src/variogram.rs:74-87
+    v.dim = dim; v.nf = n_fields; v.M = n_points; v.nb = n_bins; v.nd = 0;
+    v.f = f; v.fs0 = f_s0; v.fs1 = f_s1;
+    v.edges = bin_edges; v.es = edges_s;
+    v.pos = pos; v.ps0 = pos_s0; v.ps1 = pos_s1;
+    v.cressie = estimator_type == 'c';                                       // src/variogram.rs:24-38
+    v.variogram = variogram; v.counts = counts;
+    return run_variogram_pairs(v);
+}
+
+int gsf_variogram_directional(int dim, int64_t n_fields, int64_t n_points, int64_t n_bins, int64_t n_dirs,
+                              const double *f, int64_t f_s0, int64_t f_s1, const double *bin_edges,
+                              int64_t edges_s, const double *pos, int64_t pos_s0, int64_t pos_s1,
+                              const double *direction, int64_t dir_s0, int64_t dir_s1, double angles_tol,
+                              double bandwidth, int separate_dirs, char estimator_type, double *variogram,
+                              uint64_t *counts, int num_threads)
+{
+    (void)num_threads;
+    VarioProblem v{};
+    v.mode = gsf::kVarDirectional;
+    v.dim = dim; v.nf = n_fields; v.M = n_points; v.nb = n_bins; v.nd = n_dirs;
+    v.f = f; v.fs0 = f_s0; v.fs1 = f_s1;
+    v.edges = bin_edges; v.es = edges_s;
+    v.pos = pos; v.ps0 = pos_s0; v.ps1 = pos_s1;
+    v.dir = direction; v.ds0 = dir_s0; v.ds1 = dir_s1;
+    v.angles_tol = angles_tol; v.bandwidth = bandwidth; v.separate = separate_dirs != 0;
+    v.cressie = estimator_type == 'c';
+    v.variogram = variogram; v.counts = counts;
+    return run_variogram_pairs(v);
+}
+
+int gsf_debug_variogram_thresholds(double edge, double angles_tol, double *sqrt_thr, double *acos_thr)
+{
+    if (sqrt_thr) *sqrt_thr = sqrt_threshold(edge);
+    if (acos_thr) *acos_thr = acos_threshold(angles_tol);
+    return GSF_OK;
 }
 
 int gsf_summate_ex(const gsf_request *r)

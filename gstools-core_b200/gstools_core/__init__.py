@@ -104,6 +104,17 @@ def _load():
     L.gsf_dmma_peak.argtypes = L.gsf_dfma_peak.argtypes
     L.gsf_dmma_peak.restype = _int
     L.gsf_last_error.restype = ctypes.c_char_p
+    _a2, _a1 = [_vp, _i64, _i64], [_vp, _i64]
+    L.gsf_variogram_structured.argtypes = [_i64, _i64] + _a2 + _a2 + [ctypes.c_char, _vp, _int]
+    L.gsf_variogram_unstructured.argtypes = ([_int, _i64, _i64, _i64] + _a2 + _a1 + _a2
+                                             + [ctypes.c_char, ctypes.c_char, _vp, _vp, _int])
+    L.gsf_variogram_directional.argtypes = ([_int, _i64, _i64, _i64, _i64] + _a2 + _a1 + _a2 + _a2
+                                            + [ctypes.c_double, ctypes.c_double, _int, ctypes.c_char, _vp, _vp, _int])
+    L.gsf_debug_variogram_thresholds.argtypes = [ctypes.c_double, ctypes.c_double,
+                                                 ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+    for name in ("gsf_variogram_structured", "gsf_variogram_unstructured", "gsf_variogram_directional",
+                 "gsf_debug_variogram_thresholds"):
+        getattr(L, name).restype = _int
     for name in ("gsf_summate", "gsf_summate_incompr", "gsf_summate_fourier", "gsf_summate_on_stream",
                  "gsf_summate_ex", "gsf_set_grid_detection",
                  "gsf_set_devices", "gsf_shard_bounds", "gsf_host_alloc", "gsf_host_free", "gsf_set_chunk_points", "gsf_set_variant", "gsf_set_profiling",
@@ -406,24 +417,113 @@ def calc_field_krige_and_variance(krige_mat, krig_vecs, cond, num_threads=None):
 
 
 # ---------------------------------------------------------------------------------------------
-# OUT OF SCOPE: the variogram estimators of the reference module (src/lib.rs:120-216).  The names
-# exist only so that `from gstools_core import variogram_structured, ...` in GSTools keeps
-# importing when this module stands in for the Rust wheel; calling them fails loudly.
+# empirical variograms (reference: src/variogram.rs, bindings src/lib.rs:119-216)
 
-def _out_of_scope(name, where):
-    def f(*args, **kwargs):
-        raise NotImplementedError(
-            "gstools_core (B200) does not provide %s (%s): variogram estimation is out of scope of "
-            "this build (DESIGN.md section 1); use GSTools' Cython backend for it." % (name, where))
-    f.__name__ = name
-    f.__doc__ = "Not provided by the B200 build (reference: %s)." % where
-    return f
+def _char(value, default, name):
+    # Option<char>: None -> default; pyo3 wants a str of length 1
+    if value is None:
+        return default.encode()
+    if not isinstance(value, str):
+        raise TypeError("argument '%s': 'str' expected, got %s" % (name, type(value).__name__))
+    if len(value) != 1:
+        raise ValueError("argument '%s': expected a string of length 1" % name)
+    return value.encode("utf-8")[:1]
 
 
-variogram_structured = _out_of_scope("variogram_structured", "src/lib.rs:120-131")
-variogram_ma_structured = _out_of_scope("variogram_ma_structured", "src/lib.rs:133-147")
-variogram_directional = _out_of_scope("variogram_directional", "src/lib.rs:149-186")
-variogram_unstructured = _out_of_scope("variogram_unstructured", "src/lib.rs:188-216")
+def _host(arr, name):
+    if arr.device:
+        raise TypeError("argument '%s': the variogram estimators take host (numpy) arrays" % name)
+    return arr
+
+
+def _variogram_structured(f, mask, estimator_type, num_threads):
+    L = _load()
+    fa = _host(_Arr(f, 2, "f"), "f")
+    est = _char(estimator_type, "m", "estimator_type")
+    n0, n1 = fa.shape
+    margs = (None, 0, 0)
+    if mask is not None:
+        if not isinstance(mask, np.ndarray):
+            raise TypeError("argument 'mask': 'ndarray' expected, got %s" % type(mask).__name__)
+        if mask.dtype != np.bool_:
+            raise TypeError("argument 'mask': type mismatch: expected bool, got %s" % mask.dtype)
+        if mask.ndim != 2:
+            raise TypeError("argument 'mask': dimensionality mismatch: expected 2, got %d" % mask.ndim)
+        if mask.shape != (n0, n1):
+            # the reference panics inside ndarray's Zip::and (src/variogram.rs:218-221)
+            raise ValueError("mask has shape %s, f has %s" % (mask.shape, (n0, n1)))
+        margs = (mask.ctypes.data, mask.strides[0], mask.strides[1])
+    out = np.empty(max(n0, 1), dtype=np.float64)
+    out[0] = 0.0   # size 0 still yields [0.0] (src/variogram.rs:144-146)
+    if n0 > 0:
+        rc = L.gsf_variogram_structured(n0, n1, *fa.args(), *margs, est, out.ctypes.data, _threads(num_threads))
+        if rc:
+            _raise(rc)
+    return out
+
+
+def variogram_structured(f, estimator_type=None, num_threads=None):
+    """Variogram along axis 0 of a structured field (reference: variogram_structured_py,
+    src/lib.rs:119-131 -> src/variogram.rs:136-178).  estimator_type 'm' (default) or 'c'."""
+    return _variogram_structured(f, None, estimator_type, num_threads)
+
+
+def variogram_ma_structured(f, mask, estimator_type=None, num_threads=None):
+    """Masked structured variogram (reference: variogram_ma_structured_py, src/lib.rs:133-147 ->
+    src/variogram.rs:190-240).  mask: bool array of f's shape, True = excluded."""
+    if mask is None:
+        raise TypeError("argument 'mask': 'ndarray' expected, got NoneType")
+    return _variogram_structured(f, mask, estimator_type, num_threads)
+
+
+def variogram_unstructured(f, bin_edges, pos, estimator_type=None, distance_type=None, num_threads=None):
+    """Isotropic variogram of scattered data (reference: variogram_unstructured_py,
+    src/lib.rs:188-216 -> src/variogram.rs:465-545).  Returns (variogram (n_bins,) float64,
+    counts (n_bins,) uint64).  distance_type 'e' (default) Euclid, else Haversine (pos in degrees)."""
+    L = _load()
+    fa, e, p = _host(_Arr(f, 2, "f"), "f"), _host(_Arr(bin_edges, 1, "bin_edges"), "bin_edges"), _host(_Arr(pos, 2, "pos"), "pos")
+    est, dist = _char(estimator_type, "m", "estimator_type"), _char(distance_type, "e", "distance_type")
+    if p.shape[1] != fa.shape[1]:
+        raise ValueError("len(pos) = %d != len(f) = %d" % (p.shape[1], fa.shape[1]))       # src/variogram.rs:473-479
+    if e.shape[0] < 2:
+        raise ValueError("len(bin_edges) = %d < 2 too small" % e.shape[0])                 # :480-484
+    nb = e.shape[0] - 1
+    v, c = np.empty(nb, dtype=np.float64), np.empty(nb, dtype=np.uint64)
+    rc = L.gsf_variogram_unstructured(p.shape[0], fa.shape[0], fa.shape[1], nb, *fa.args(), *e.args(), *p.args(),
+                                      est, dist, v.ctypes.data, c.ctypes.data, _threads(num_threads))
+    if rc:
+        _raise(rc)
+    return v, c
+
+
+def variogram_directional(f, bin_edges, pos, direction, angles_tol=None, bandwidth=None, separate_dirs=None,
+                          estimator_type=None, num_threads=None):
+    """Directional variogram of scattered data (reference: variogram_directional_py,
+    src/lib.rs:149-186 -> src/variogram.rs:315-447).  direction: (n_dirs, dim), normed.  Defaults
+    as in the binding: angles_tol pi/8, bandwidth -1 (off), separate_dirs False.  Returns
+    (variogram, counts), both (n_dirs, n_bins)."""
+    L = _load()
+    fa, e, p = _host(_Arr(f, 2, "f"), "f"), _host(_Arr(bin_edges, 1, "bin_edges"), "bin_edges"), _host(_Arr(pos, 2, "pos"), "pos")
+    dr = _host(_Arr(direction, 2, "direction"), "direction")
+    est = _char(estimator_type, "m", "estimator_type")
+    tol = float(np.pi / 8.0 if angles_tol is None else angles_tol)
+    bw = float(-1.0 if bandwidth is None else bandwidth)
+    if p.shape[0] != dr.shape[1]:
+        raise ValueError("dim(pos) = %d != dim(direction) = %d" % (p.shape[0], dr.shape[1]))   # src/variogram.rs:326-332
+    if p.shape[1] != fa.shape[1]:
+        raise ValueError("len(pos) = %d != len(f) = %d" % (p.shape[1], fa.shape[1]))           # :333-339
+    if e.shape[0] < 2:
+        raise ValueError("len(bin_edges) = %d < 2 too small" % e.shape[0])                     # :340-344
+    if not tol > 0.0:
+        raise ValueError("tolerance for angle search masks must be > 0")                       # :345-348
+    nb, nd = e.shape[0] - 1, dr.shape[0]
+    v, c = np.empty((nd, nb), dtype=np.float64), np.empty((nd, nb), dtype=np.uint64)
+    rc = L.gsf_variogram_directional(p.shape[0], fa.shape[0], fa.shape[1], nb, nd, *fa.args(), *e.args(), *p.args(),
+                                     *dr.args(), tol, bw, int(bool(separate_dirs)), est, v.ctypes.data,
+                                     c.ctypes.data, _threads(num_threads))
+    if rc:
+        _raise(rc)
+    return v, c
 
 
 # ---------------------------------------------------------------------------------------------

@@ -145,6 +145,39 @@ int gsf_krige(int64_t n_cond, int64_t n_points,
               const double *cond, int64_t cond_s,
               double *field, double *error, int num_threads);
 
+/* ---- empirical variograms (reference: src/variogram.rs; bindings src/lib.rs:119-216) -------- */
+
+/* estimator_type: 'c' = Cressie, anything else = Matheron (src/variogram.rs:22-39).  Host-resident
+ * arrays with element strides (mask: byte strides == element strides of a bool array).  Counts are
+ * exact; for Euclidean distances every pair lands in the bin(s) the reference puts it in (see
+ * gsf_variogram_kernels.cuh); the sums run in a fixed, run-to-run deterministic order that differs
+ * from the reference's sequential one (relative difference ~1e-15).
+ *
+ * variogram_structured / variogram_ma_structured (src/variogram.rs:136-178, :190-240): f is
+ * (n0, n1), mask NULL or (n0, n1) with non-zero = masked; variogram gets n0 entries, [0] = 0. */
+int gsf_variogram_structured(int64_t n0, int64_t n1, const double *f, int64_t f_s0, int64_t f_s1,
+                             const uint8_t *mask, int64_t mask_s0, int64_t mask_s1, char estimator_type,
+                             double *variogram, int num_threads);
+/* variogram_unstructured (src/variogram.rs:465-545): f (n_fields, n_points), bin_edges (n_bins + 1),
+ * pos (dim, n_points), dim 1..3; distance_type 'e' = Euclid, anything else = Haversine (dim 2,
+ * degrees).  variogram and counts get n_bins entries.  NaN field differences are skipped. */
+int gsf_variogram_unstructured(int dim, int64_t n_fields, int64_t n_points, int64_t n_bins, const double *f,
+                               int64_t f_s0, int64_t f_s1, const double *bin_edges, int64_t edges_s,
+                               const double *pos, int64_t pos_s0, int64_t pos_s1, char estimator_type,
+                               char distance_type, double *variogram, uint64_t *counts, int num_threads);
+/* variogram_directional (src/variogram.rs:315-447): direction is (n_dirs, dim), expected normed;
+ * variogram and counts are (n_dirs, n_bins) row-major.  angles_tol must be > 0; bandwidth <= 0
+ * disables the band test; separate_dirs stops at the first matching direction. */
+int gsf_variogram_directional(int dim, int64_t n_fields, int64_t n_points, int64_t n_bins, int64_t n_dirs,
+                              const double *f, int64_t f_s0, int64_t f_s1, const double *bin_edges,
+                              int64_t edges_s, const double *pos, int64_t pos_s0, int64_t pos_s1,
+                              const double *direction, int64_t dir_s0, int64_t dir_s1, double angles_tol,
+                              double bandwidth, int separate_dirs, char estimator_type, double *variogram,
+                              uint64_t *counts, int num_threads);
+/* Host logic of the bit-faithful binning (no device needed): min{x : sqrt(x) >= edge} and
+ * max{a in [0,1) : acos(a) >= angles_tol} (-1 if none).  Either output may be NULL. */
+int gsf_debug_variogram_thresholds(double edge, double angles_tol, double *sqrt_thr, double *acos_thr);
+
 /* Host-logic introspection for tests (no device needed): the pipeline chunk sizes for n_points
  * host-resident points (returns the count, or -count if max_sizes is too small), and the exact
  * structured-grid detector (returns 1 and the axis lengths, or 0). */

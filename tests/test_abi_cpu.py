@@ -125,8 +125,44 @@ def test_krige_surface_and_validation():
             gc.calc_field_krige(mat, vecs, cond)
 
 
-def test_variogram_names_fail_loudly():
-    # out of scope: importable for GSTools, but never a silent fallback
-    for name in ("variogram_structured", "variogram_ma_structured", "variogram_directional", "variogram_unstructured"):
-        with pytest.raises(NotImplementedError, match="out of scope"):
-            getattr(gc, name)(np.ones((3, 3)))
+def test_variogram_surface_and_validation():
+    # src/lib.rs:119-216: names, positional order and Option<> defaults of the four bindings
+    import inspect
+    assert list(inspect.signature(gc.variogram_structured).parameters) == ["f", "estimator_type", "num_threads"]
+    assert list(inspect.signature(gc.variogram_ma_structured).parameters) == [
+        "f", "mask", "estimator_type", "num_threads"]
+    assert list(inspect.signature(gc.variogram_directional).parameters) == [
+        "f", "bin_edges", "pos", "direction", "angles_tol", "bandwidth", "separate_dirs", "estimator_type",
+        "num_threads"]
+    assert list(inspect.signature(gc.variogram_unstructured).parameters) == [
+        "f", "bin_edges", "pos", "estimator_type", "distance_type", "num_threads"]
+    f = np.ones((1, 5)); pos = np.ones((2, 5)); edges = np.linspace(0.0, 1.0, 4)
+    with pytest.raises(TypeError):
+        gc.variogram_structured(np.ones((3, 3), dtype=np.float32))
+    with pytest.raises(TypeError):
+        gc.variogram_ma_structured(np.ones((3, 3)), np.zeros((3, 3)))          # mask must be bool
+    with pytest.raises(ValueError):
+        gc.variogram_ma_structured(np.ones((3, 3)), np.zeros((3, 2), dtype=bool))
+    with pytest.raises(ValueError):
+        gc.variogram_structured(np.ones((3, 3)), "mm")                         # Option<char>
+    with pytest.raises(ValueError):
+        gc.variogram_unstructured(f, edges, np.ones((2, 4)))                   # src/variogram.rs:473
+    with pytest.raises(ValueError):
+        gc.variogram_unstructured(f, np.array([1.0]), pos)                     # :480
+    with pytest.raises(ValueError):
+        gc.variogram_directional(f, edges, pos, np.ones((1, 3)))               # :326
+    with pytest.raises(ValueError):
+        gc.variogram_directional(f, edges, pos, np.ones((1, 2)), angles_tol=0.0)   # :345
+    # an empty field never reaches the device: [0.0] (src/variogram.rs:144-146)
+    assert gc.variogram_structured(np.ones((0, 3))).tolist() == [0.0]
+
+
+@pytest.mark.skipif(HAVE_GPU, reason="checks the no-device failure mode")
+def test_variograms_fail_loudly_without_device():
+    f = np.ones((1, 5)); pos = np.ones((2, 5)); edges = np.linspace(0.0, 1.0, 4)
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        gc.variogram_structured(np.ones((4, 3)))
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        gc.variogram_unstructured(f, edges, pos)
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        gc.variogram_directional(f, edges, pos, np.array([[1.0, 0.0]]))

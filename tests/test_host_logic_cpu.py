@@ -81,3 +81,37 @@ def test_detect_grid_rejects():
     # -0.0 vs +0.0 differ bitwise: treated as a mismatch (falls back to the general kernel)
     q = pos.copy(); q[1, 5] = -0.0
     assert pos[1, 5] == 0.0 and q[1, 5] == pos[1, 5] and detect(q) is None
+
+
+def _thresholds(edge, tol=1.0):
+    a, b = ctypes.c_double(), ctypes.c_double()
+    assert L.gsf_debug_variogram_thresholds(ctypes.c_double(edge), ctypes.c_double(tol), ctypes.byref(a),
+                                              ctypes.byref(b)) == 0
+    return a.value, b.value
+
+
+def test_variogram_sqrt_threshold_is_exact():
+    # t(e) = min{x : sqrt(x) >= e}: what makes `d2 >= t(e)` the same test as `sqrt(d2) >= e`
+    # (gsf_variogram_kernels.cuh; reference comparison src/variogram.rs:397,518)
+    rng = np.random.default_rng(7)
+    edges = np.concatenate([10.0 ** rng.uniform(-300, 150, 400), rng.uniform(0, 10, 400),
+                            [1.0, 2.0, 3.0, 5.0 / 3.0, 1e-320, 5e-324, 1.3e154, 1.5e154, 1.7976931348623157e308]])
+    for e in edges:
+        t, _ = _thresholds(float(e))
+        assert np.sqrt(t) >= e
+        assert t == 0.0 or np.sqrt(np.nextafter(t, 0.0)) < e
+    assert _thresholds(0.0)[0] == 0.0 and _thresholds(-3.0)[0] == 0.0
+    assert _thresholds(np.inf)[0] == np.inf and np.isnan(_thresholds(np.nan)[0])
+
+
+def test_variogram_acos_threshold_is_exact():
+    # a*(tol) = max{a in [0,1) : acos(a) >= tol}: `angle <= a*` replaces `acos(angle) >= tol`
+    # (reference: src/variogram.rs:281-285)
+    import math
+    for tol in [math.pi / 8, math.pi / 4, 1e-3, 1e-9, 1.0, math.pi / 2, 0.3]:
+        _, a = _thresholds(1.0, tol)
+        assert 0.0 <= a < 1.0 and math.acos(a) >= tol
+        nxt = float(np.nextafter(a, 2.0))
+        assert nxt >= 1.0 or math.acos(nxt) < tol
+    assert _thresholds(1.0, 2.0)[1] == -1.0            # acos(a) <= pi/2 < tol for every a >= 0: never rejected
+    assert _thresholds(1.0, 1e-300)[1] == float(np.nextafter(1.0, 0.0))

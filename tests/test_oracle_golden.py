@@ -3,6 +3,8 @@
 The reference asserts bitwise equality for summator and summator_fourier and <= 6 ulp (or
 <= f64::EPSILON absolute, approx's ulps_eq) for summator_incompr; the oracle must meet the same.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -88,3 +90,61 @@ def test_krige_golden_6ulp(krige_kat):
     assert _ulps_eq(e, krige_kat["error"]).all(), ulp_diff(e, krige_kat["error"])      # :210-220
     f2 = oracle.calc_field_krige(krige_kat["krig_mat"], krige_kat["krig_vecs"], krige_kat["cond"])
     assert np.array_equal(f, f2)                                                      # :228-244
+
+
+# ---- variogram estimators: the reference's own tests, src/variogram.rs:577-842 -----------------
+
+@pytest.fixture(scope="module")
+def vkat():
+    import json
+    with open(os.path.join(os.path.dirname(__file__), "golden", "variogram_rs_kat.json")) as fh:
+        return json.load(fh)
+
+
+def ulps(a, b):
+    return int(ulp_diff(a, b).max())
+
+
+def _vsetup(vkat):
+    pos = np.stack([np.arange(0.0, 10.0, 1.0), np.arange(0.0, 10.0, 1.0)])       # :672-676
+    return pos, np.array([vkat["unstruct_field"]]), np.linspace(0.0, 5.0, 4)     # :677-689
+
+
+def test_variogram_structured_golden(vkat):
+    f = np.array(vkat["struct_field"]).reshape(-1, 1)
+    assert ulps(oracle.variogram_structured(f, "m"), np.array(vkat["struct_gamma"])) <= vkat["max_ulps"]
+    no_mask = np.zeros((10, 1), dtype=bool)
+    assert ulps(oracle.variogram_ma_structured(f, no_mask, "m"), np.array(vkat["struct_gamma"])) <= vkat["max_ulps"]
+    mask2 = np.array(vkat["ma_struct_mask2"]).reshape(-1, 1)
+    assert ulps(oracle.variogram_ma_structured(f, mask2, "m"), np.array(vkat["ma_struct_gamma2"])) <= vkat["max_ulps"]
+
+
+def test_variogram_unstructured_golden(vkat):
+    pos, f, edges = _vsetup(vkat)
+    gamma, cnts = oracle.variogram_unstructured(f, edges, pos, "m", "e")
+    assert ulps(gamma, np.array(vkat["unstruct_gamma"])) <= vkat["max_ulps"]
+    assert cnts.tolist() == vkat["unstruct_counts"]
+
+
+def test_variogram_directional_golden(vkat):
+    pos, f, edges = _vsetup(vkat)
+    direction = np.array([[0.0, np.pi], [0.0, 0.0]])                             # :821
+    gamma, cnts = oracle.variogram_directional(f, edges, pos, direction, np.pi / 8.0, -1.0, False, "m")
+    assert ulps(gamma, np.array(vkat["directional_gamma"])) <= vkat["max_ulps"]
+    assert cnts.tolist() == vkat["directional_counts"]
+
+
+def test_variogram_multi_field_property(vkat):
+    # src/variogram.rs:711-816: the multi-field estimate is the mean of the single-field ones
+    pos, f, edges = _vsetup(vkat)
+    f2 = np.array([vkat["unstruct_field2"]])
+    both = np.concatenate([f, f2])
+    g1, _ = oracle.variogram_unstructured(f, edges, pos, "m", "e")
+    g2, _ = oracle.variogram_unstructured(f2, edges, pos, "m", "e")
+    gm, _ = oracle.variogram_unstructured(both, edges, pos, "m", "e")
+    assert ulps(gm, 0.5 * (g1 + g2)) <= vkat["max_ulps"]
+    direction = np.array([[0.0, np.pi], [0.0, 0.0]])
+    d1, _ = oracle.variogram_directional(f, edges, pos, direction)
+    d2, _ = oracle.variogram_directional(f2, edges, pos, direction)
+    dm, _ = oracle.variogram_directional(both, edges, pos, direction)
+    assert ulps(dm, 0.5 * (d1 + d2)) <= vkat["max_ulps"]
