@@ -6,11 +6,15 @@
 //   estimators Matheron / Cressie :41-65, distances Euclid / Haversine :92-123.
 //
 // The reference walks ALL point pairs once per bin (it parallelises over bins).  Here every pair
-// is visited once: a CTA owns 128 "i" points (one per thread, in registers) and streams chunks of
-// "j" points through shared memory; each in-range pair is binned by binary search and added to a
-// PER-THREAD (bin, direction) accumulator in shared memory (layout [slot][thread]: no atomics, no
-// bank conflicts, and every thread's summation order is fixed).  Threads, then CTAs, are combined
-// in a fixed order, so the result is run-to-run deterministic.
+// is visited at most once: the host sorts the points along a Morton curve and lists the tiles
+// (128 "i" points x one chunk of "j" points) whose bounding boxes are close enough to hold an
+// in-range pair (gsf_variogram_host.inc).  A CTA keeps one i point per thread in registers and
+// streams the j chunk through shared memory; the range test of 8 j points runs back to back (pure
+// FP64 arithmetic, no divergence), then only the candidates are binned by binary search and added
+// to a PER-THREAD (bin, direction) accumulator in shared memory (layout [slot][thread]: no
+// atomics, no bank conflicts, and every thread's summation order is fixed).  Threads, then CTAs,
+// are combined in a fixed order, so the result is run-to-run deterministic.  Every term of the
+// estimators is symmetric in (i, j) bit for bit, so the reordering only changes the summation order.
 //
 // Bin membership is bit-faithful to the reference for Euclidean distances: instead of comparing
 // sqrt(d2) with an edge e, the kernel compares the squared distance d2 -- accumulated exactly like
@@ -26,8 +30,12 @@
 namespace gsf {
 
 constexpr int kVarThreads = 128;
+constexpr int kVarBatch = 8;       // j points whose range test runs back to back before any binning
 
 enum VarioMode { kVarEuclid = 0, kVarHaversine = 1, kVarDirectional = 2 };
+
+// shared-memory record of one j point: D = 1: (x, f); D = 2: (x, y, f, cos(lat)); D = 3: (x, y, z, f)
+__host__ __device__ constexpr int vario_rec(int d) { return d == 1 ? 2 : 4; }
 
 struct VarioArgs {
     const double *pos;     // [D][m]
@@ -37,6 +45,8 @@ struct VarioArgs {
     const double *thr;     // [nb + 1] thresholds on d2 (Euclid / directional) or raw edges (Haversine)
     int nb;                // bins handled by this launch
     int monotone;          // thresholds are non-decreasing and free of NaN: one bin per pair
+    double pre_lo, pre_hi; // range pre-filter: a pair with key < pre_lo or key >= pre_hi is in no bin
+                           // (thr[0], thr[nb] when monotone, else NaN = filter nothing)
     int n_dir;             // directional only
     const double *dir;     // [n_dir][D]
     int use_bw;            // bandwidth > 0 (src/variogram.rs:262)
@@ -45,10 +55,10 @@ struct VarioArgs {
     int separate;
     int cressie;
     int jc;                // points per j chunk (multiple of 128)
-    int n_iblocks;
     int64_t n_tiles;
-    const int64_t *tile_prefix;   // [n_iblocks + 1]: first tile of every i block
-    double *part_v;               // [gridDim.x][slots]
+    const int2 *tiles;     // (i block, j chunk) of every tile that can hold an in-range pair
+    int flush_every;       // tiles after which the 32-bit per-thread counts move to the 64-bit totals
+    double *part_v;        // [gridDim.x][slots]
     unsigned long long *part_c;
 };
 
@@ -57,157 +67,182 @@ __device__ __forceinline__ double vario_estimate(int cressie, double d)
     return cressie ? __dsqrt_rn(fabs(d)) : __dmul_rn(d, d);   // src/variogram.rs:57-59 / 44-46
 }
 
+// distance key of the pair (xi, record pj): squared Euclidean distance accumulated like Euclid::dist
+// (src/variogram.rs:93-102, no FMA), or the Haversine distance itself (:108-117)
+template <int D, int MODE>
+__device__ __forceinline__ double vario_key(const double (&xi)[D], double cos_i, const double *pj, double (&df)[D])
+{
+#pragma unroll
+    for (int q = 0; q < D; ++q) df[q] = xi[q] - pj[q];
+    if (MODE == kVarHaversine) {
+        const double kRad = 0.017453292519943295;   // f64::to_radians: x * (PI / 180)
+        const double s1 = sin(__dmul_rn(df[0], kRad) / 2.0), s2 = sin(__dmul_rn(df[D - 1], kRad) / 2.0);
+        const double arg = __dadd_rn(__dmul_rn(s1, s1), __dmul_rn(__dmul_rn(cos_i, pj[3 % vario_rec(D)]), __dmul_rn(s2, s2)));
+        return 2.0 * atan2(__dsqrt_rn(arg), __dsqrt_rn(__dadd_rn(1.0, -arg)));
+    }
+    double key = __dmul_rn(df[0], df[0]);
+#pragma unroll
+    for (int q = 1; q < D; ++q) key = __dadd_rn(key, __dmul_rn(df[q], df[q]));
+    return key;
+}
+
 template <int D, int MODE>
 __global__ void __launch_bounds__(kVarThreads) gsf_vario_pairs(VarioArgs a)
 {
+    constexpr int W = vario_rec(D);
     extern __shared__ __align__(16) unsigned char vsm[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_dir = MODE == kVarDirectional ? a.n_dir : 1;
     const int nb = a.nb, slots = n_dir * nb, jc = a.jc;
-    double *acc_v = reinterpret_cast<double *>(vsm);                                        // [slots][128]
-    unsigned long long *acc_c = reinterpret_cast<unsigned long long *>(acc_v + (size_t)slots * kVarThreads);
-    double *s_thr = reinterpret_cast<double *>(acc_c + (size_t)slots * kVarThreads);        // [nb + 1]
-    double *s_dir = s_thr + nb + 1;                                                         // [n_dir][D]
-    double *s_pos = s_dir + n_dir * D;                                                      // [D][jc]
-    double *s_f = s_pos + D * jc;                                                           // [jc]
-    double *s_cos = s_f + jc;                                                               // [jc] (Haversine)
-    __shared__ int64_t s_tile[2];
+    double *s_rec = reinterpret_cast<double *>(vsm);                                    // [jc][W]
+    double *acc_v = s_rec + (size_t)jc * W;                                             // [slots][128]
+    double *s_thr = acc_v + (size_t)slots * kVarThreads;                                // [nb + 1]
+    double *s_dir = s_thr + nb + 1;                                                     // [n_dir][D]
+    unsigned long long *tot_c = reinterpret_cast<unsigned long long *>(s_dir + n_dir * D);   // [slots]
+    unsigned int *acc_c = reinterpret_cast<unsigned int *>(tot_c + slots);              // [slots][128]
 
     for (int s = 0; s < slots; ++s) {
         acc_v[s * kVarThreads + tid] = 0.0;
-        acc_c[s * kVarThreads + tid] = 0ull;
+        acc_c[s * kVarThreads + tid] = 0u;
     }
+    for (int s = tid; s < slots; s += kVarThreads) tot_c[s] = 0ull;
     for (int e = tid; e <= nb; e += kVarThreads) s_thr[e] = a.thr[e];
     if (MODE == kVarDirectional)
         for (int e = tid; e < n_dir * D; e += kVarThreads) s_dir[e] = a.dir[e];
 
-    const double kRad = 0.017453292519943295;   // f64::to_radians: x * (PI / 180)
     const int64_t m = a.m;
     const bool one_field = a.nf == 1;
+    const double pre_lo = a.pre_lo, pre_hi = a.pre_hi;
+    int since_flush = 0;
+
+    // 32-bit per-thread counts -> 64-bit CTA totals (integer sums: any schedule gives the same result)
+    auto flush_counts = [&]() {
+        __syncthreads();
+        for (int s = warp; s < slots; s += kVarThreads / 32) {
+            unsigned int *pc = acc_c + s * kVarThreads;
+            unsigned long long c = (unsigned long long)pc[lane] + pc[lane + 32] + pc[lane + 64] + pc[lane + 96];
+            pc[lane] = pc[lane + 32] = pc[lane + 64] = pc[lane + 96] = 0u;
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            if (lane == 0) tot_c[s] += c;
+        }
+        __syncthreads();
+    };
 
     for (int64_t t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
-        if (tid == 0) {   // largest i block whose first tile is <= t
-            int lo = 0, hi = a.n_iblocks;
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (a.tile_prefix[mid] <= t) lo = mid; else hi = mid;
-            }
-            s_tile[0] = lo;
-            s_tile[1] = ((int64_t)lo * kVarThreads + 1) / jc + (t - a.tile_prefix[lo]);
-        }
-        __syncthreads();   // tile known; everybody is done with the previous chunk
-        const int64_t i = s_tile[0] * kVarThreads + tid;
-        const int64_t j0 = s_tile[1] * jc;
+        const int2 tile = a.tiles[t];
+        const int64_t i = (int64_t)tile.x * kVarThreads + tid;
+        const int64_t j0 = (int64_t)tile.y * jc;
         const int cnt = (int)(m - j0 < jc ? m - j0 : jc);
+        __syncthreads();   // everybody is done with the previous chunk
         for (int e = tid; e < cnt; e += kVarThreads) {
+            double *r = s_rec + e * W;
 #pragma unroll
-            for (int q = 0; q < D; ++q) s_pos[q * jc + e] = a.pos[q * m + j0 + e];
-            if (one_field) s_f[e] = a.f[j0 + e];
-            if (MODE == kVarHaversine) s_cos[e] = cos(a.pos[j0 + e] * kRad);
+            for (int q = 0; q < D; ++q) r[q] = a.pos[q * m + j0 + e];
+            r[D] = one_field ? a.f[j0 + e] : 0.0;
+            if (MODE == kVarHaversine) r[3] = cos(a.pos[j0 + e] * 0.017453292519943295);
         }
         const bool valid = i < m;
         double xi[D], fi = 0.0, cos_i = 0.0;
 #pragma unroll
         for (int q = 0; q < D; ++q) xi[q] = valid ? a.pos[q * m + i] : 0.0;
         if (valid && one_field) fi = a.f[i];
-        if (valid && MODE == kVarHaversine) cos_i = cos(xi[0] * kRad);
+        if (valid && MODE == kVarHaversine) cos_i = cos(xi[0] * 0.017453292519943295);
         __syncthreads();
-        if (!valid) continue;
-        int jj = j0 <= i ? (int)(i + 1 - j0 < cnt ? i + 1 - j0 : cnt) : 0;   // only pairs j > i
-#pragma unroll 2
-        for (; jj < cnt; ++jj) {
-            double df[D], key;
+        // only pairs j > i; lanes past the end of the data own no pair
+        const int jstart = !valid ? cnt : j0 > i ? 0 : (int)(i + 1 - j0 < cnt ? i + 1 - j0 : cnt);
+        const int jb0 = __shfl_sync(0xffffffffu, jstart, 0) / kVarBatch * kVarBatch;   // lane 0 starts first
+        for (int jb = jb0; jb < cnt; jb += kVarBatch) {
+            unsigned mask = 0u;
 #pragma unroll
-            for (int q = 0; q < D; ++q) df[q] = xi[q] - s_pos[q * jc + jj];
-            if (MODE == kVarHaversine) {   // src/variogram.rs:108-117
-                const double s1 = sin(__dmul_rn(df[0], kRad) / 2.0), s2 = sin(__dmul_rn(df[D - 1], kRad) / 2.0);
-                const double arg = __dadd_rn(__dmul_rn(s1, s1),
-                                             __dmul_rn(__dmul_rn(cos_i, s_cos[jj]), __dmul_rn(s2, s2)));
-                key = 2.0 * atan2(__dsqrt_rn(arg), __dsqrt_rn(__dadd_rn(1.0, -arg)));
-            } else {                       // Euclid::dist without the sqrt, src/variogram.rs:93-102
-                key = __dmul_rn(df[0], df[0]);
-#pragma unroll
-                for (int q = 1; q < D; ++q) key = __dadd_rn(key, __dmul_rn(df[q], df[q]));
+            for (int u = 0; u < kVarBatch; ++u) {
+                double df[D];
+                const double key = vario_key<D, MODE>(xi, cos_i, s_rec + (jb + u) * W, df);
+                // candidate unless excluded from every bin (src/variogram.rs:397 / :518); NaN stays in
+                const bool in = jb + u >= jstart && jb + u < cnt && !(key < pre_lo) && !(key >= pre_hi);
+                mask |= (unsigned)in << u;
             }
-            // bins b with !(key < thr[b] || key >= thr[b+1])  (src/variogram.rs:397 / :518)
-            int b_lo, b_hi;
-            const bool searched = a.monotone && key == key;
-            if (searched) {
-                if (key < s_thr[0] || key >= s_thr[nb]) continue;
-                int lo = 0, hi = nb;
-                while (hi - lo > 1) {
-                    const int mid = (lo + hi) >> 1;
-                    if (s_thr[mid] <= key) lo = mid; else hi = mid;
-                }
-                b_lo = lo;
-                b_hi = lo + 1;
-            } else {
-                b_lo = 0;
-                b_hi = nb;
-            }
-            for (int b = b_lo; b < b_hi; ++b) {
-                if (!searched && (key < s_thr[b] || key >= s_thr[b + 1])) continue;
-                for (int r = 0; r < n_dir; ++r) {
-                    if (MODE == kVarDirectional) {   // dir_test, src/variogram.rs:243-290
-                        const double *dr = s_dir + r * D;
-                        double s_prod = __dmul_rn(df[0], dr[0]);
-#pragma unroll
-                        for (int q = 1; q < D; ++q) s_prod = __dadd_rn(s_prod, __dmul_rn(df[q], dr[q]));
-                        if (a.use_bw) {
-                            double b2 = 0.0;
-#pragma unroll
-                            for (int q = 0; q < D; ++q) {
-                                const double u = __dadd_rn(df[q], -__dmul_rn(s_prod, dr[q]));
-                                b2 = q == 0 ? __dmul_rn(u, u) : __dadd_rn(b2, __dmul_rn(u, u));
-                            }
-                            if (b2 >= a.bw_thr) continue;
-                        }
-                        if (key > 0.0) {
-                            const double angle = __ddiv_rn(fabs(s_prod), __dsqrt_rn(key));
-                            if (angle <= a.ang_thr) continue;
-                        }
+            while (mask) {
+                const int jj = jb + __ffs(mask) - 1;
+                mask &= mask - 1;
+                const double *pj = s_rec + jj * W;
+                double df[D];
+                const double key = vario_key<D, MODE>(xi, cos_i, pj, df);
+                // bins b with !(key < thr[b] || key >= thr[b+1])
+                int b_lo = 0, b_hi = nb;
+                const bool searched = a.monotone && key == key;
+                if (searched) {
+                    int lo = 0, hi = nb;   // thr[lo] <= key < thr[hi]
+                    while (hi - lo > 1) {
+                        const int mid = (lo + hi) >> 1;
+                        if (s_thr[mid] <= key) lo = mid; else hi = mid;
                     }
-                    const int slot = (r * nb + b) * kVarThreads + tid;
-                    if (one_field) {
-                        const double fij = fi - s_f[jj];
-                        if (fij == fij) {   // skip no-data values, src/variogram.rs:413 / :524
-                            acc_c[slot] += 1ull;
-                            acc_v[slot] = __dadd_rn(acc_v[slot], vario_estimate(a.cressie, fij));
-                        }
-                    } else {
-                        double v = acc_v[slot];
-                        unsigned long long c = acc_c[slot];
-                        for (int q = 0; q < a.nf; ++q) {
-                            const double fij = a.f[q * m + i] - a.f[q * m + j0 + jj];
-                            if (fij == fij) {
-                                c += 1ull;
-                                v = __dadd_rn(v, vario_estimate(a.cressie, fij));
+                    b_lo = lo;
+                    b_hi = lo + 1;
+                }
+                for (int b = b_lo; b < b_hi; ++b) {
+                    if (!searched && (key < s_thr[b] || key >= s_thr[b + 1])) continue;
+                    for (int r = 0; r < n_dir; ++r) {
+                        if (MODE == kVarDirectional) {   // dir_test, src/variogram.rs:243-290
+                            const double *dr = s_dir + r * D;
+                            double s_prod = __dmul_rn(df[0], dr[0]);
+#pragma unroll
+                            for (int q = 1; q < D; ++q) s_prod = __dadd_rn(s_prod, __dmul_rn(df[q], dr[q]));
+                            if (a.use_bw) {
+                                double b2 = 0.0;
+#pragma unroll
+                                for (int q = 0; q < D; ++q) {
+                                    const double w = __dadd_rn(df[q], -__dmul_rn(s_prod, dr[q]));
+                                    b2 = q == 0 ? __dmul_rn(w, w) : __dadd_rn(b2, __dmul_rn(w, w));
+                                }
+                                if (b2 >= a.bw_thr) continue;
+                            }
+                            if (key > 0.0) {
+                                const double angle = __ddiv_rn(fabs(s_prod), __dsqrt_rn(key));
+                                if (angle <= a.ang_thr) continue;
                             }
                         }
-                        acc_v[slot] = v;
-                        acc_c[slot] = c;
+                        const int slot = (r * nb + b) * kVarThreads + tid;
+                        if (one_field) {
+                            const double fij = fi - pj[D];
+                            if (fij == fij) {   // skip no-data values, src/variogram.rs:413 / :524
+                                acc_c[slot] += 1u;
+                                acc_v[slot] = __dadd_rn(acc_v[slot], vario_estimate(a.cressie, fij));
+                            }
+                        } else {
+                            double v = acc_v[slot];
+                            unsigned int c = acc_c[slot];
+                            for (int q = 0; q < a.nf; ++q) {
+                                const double fij = a.f[q * m + i] - a.f[q * m + j0 + jj];
+                                if (fij == fij) {
+                                    c += 1u;
+                                    v = __dadd_rn(v, vario_estimate(a.cressie, fij));
+                                }
+                            }
+                            acc_v[slot] = v;
+                            acc_c[slot] = c;
+                        }
+                        if (MODE == kVarDirectional && a.separate) break;   // src/variogram.rs:424-426
                     }
-                    if (MODE == kVarDirectional && a.separate) break;   // src/variogram.rs:424-426
                 }
             }
+        }
+        if (++since_flush >= a.flush_every) {
+            flush_counts();
+            since_flush = 0;
         }
     }
 
     // threads -> CTA in a fixed order: 4 columns per lane, then the xor butterfly
-    __syncthreads();
+    flush_counts();
     for (int s = warp; s < slots; s += kVarThreads / 32) {
         const double *pv = acc_v + s * kVarThreads;
-        const unsigned long long *pc = acc_c + s * kVarThreads;
         double v = ((pv[lane] + pv[lane + 32]) + pv[lane + 64]) + pv[lane + 96];
-        unsigned long long c = pc[lane] + pc[lane + 32] + pc[lane + 64] + pc[lane + 96];
 #pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) {
-            v += __shfl_xor_sync(0xffffffffu, v, o);
-            c += __shfl_xor_sync(0xffffffffu, c, o);
-        }
+        for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         if (lane == 0) {
             a.part_v[(size_t)blockIdx.x * slots + s] = v;
-            a.part_c[(size_t)blockIdx.x * slots + s] = c;
+            a.part_c[(size_t)blockIdx.x * slots + s] = tot_c[s];
         }
     }
 }
