@@ -247,6 +247,136 @@ __global__ void __launch_bounds__(kVarThreads) gsf_vario_pairs(VarioArgs a)
     }
 }
 
+// ---- isotropic Euclidean fast path -------------------------------------------------------------
+// For sorted points the distances inside one tile span only a few bins.  The host lists every tile
+// once per window of kVarWin consecutive bins its bounding boxes can reach; the kernel keeps that
+// window's thresholds in (uniform) registers: the bin of a pair is the count of window thresholds
+// below its key -- no search, no threshold loads -- and the per-thread accumulators shrink to
+// kVarWin columns of shared memory, so occupancy no longer depends on the number of bins.
+// After the tile the 128 threads are combined in a fixed order and added to the CTA's running
+// per-bin totals (global memory, touched once per tile and bin).
+constexpr int kVarWin = 8;
+
+struct VarioIsoArgs {
+    const double *pos;     // [D][m], Morton order
+    const double *f;       // [nf][m]
+    int64_t m;
+    int nf;
+    const double *thr;     // [nb + 1], non-decreasing, no NaN
+    int nb;
+    int cressie;
+    int jc;
+    int64_t n_tiles;
+    const int3 *tiles;     // (i block, j chunk, first bin of the window)
+    double *part_v;        // [gridDim.x][nb], zeroed by the host
+    unsigned long long *part_c;
+};
+
+template <int D, bool CRESSIE>
+__global__ void __launch_bounds__(kVarThreads) gsf_vario_iso(VarioIsoArgs a)
+{
+    constexpr int W = vario_rec(D), K = kVarWin;
+    extern __shared__ __align__(16) unsigned char vsm[];
+    double *s_rec = reinterpret_cast<double *>(vsm);                        // [jc][W]
+    double *w_v = s_rec + (size_t)a.jc * W;                                  // [K][128] window sums, one column per thread
+    unsigned int *w_c = reinterpret_cast<unsigned int *>(w_v + K * kVarThreads);   // [K][128]
+    __shared__ double s_wv[kVarThreads / 32][K];
+    __shared__ unsigned long long s_wc[kVarThreads / 32][K];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nb = a.nb, jc = a.jc;
+    const int64_t m = a.m;
+    const bool one_field = a.nf == 1;
+    double *cta_v = a.part_v + (size_t)blockIdx.x * nb;
+    unsigned long long *cta_c = a.part_c + (size_t)blockIdx.x * nb;
+
+    for (int64_t t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+        const int3 tile = a.tiles[t];
+        const int64_t i = (int64_t)tile.x * kVarThreads + tid;
+        const int64_t j0 = (int64_t)tile.y * jc;
+        const int b0 = tile.z;
+        const int cnt = (int)(m - j0 < jc ? m - j0 : jc);
+        __syncthreads();   // everybody is done with the previous chunk
+        for (int e = tid; e < cnt; e += kVarThreads) {
+            double *r = s_rec + e * W;
+#pragma unroll
+            for (int q = 0; q < D; ++q) r[q] = a.pos[q * m + j0 + e];
+            r[D] = one_field ? a.f[j0 + e] : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            w_v[k * kVarThreads + tid] = 0.0;
+            w_c[k * kVarThreads + tid] = 0u;
+        }
+        const bool valid = i < m;
+        double xi[D], fi = 0.0;
+#pragma unroll
+        for (int q = 0; q < D; ++q) xi[q] = valid ? a.pos[q * m + i] : 0.0;
+        if (valid && one_field) fi = a.f[i];
+        double th[K + 1];   // beyond the last edge: +inf, `key >= inf` never holds for a finite key
+#pragma unroll
+        for (int k = 0; k <= K; ++k) th[k] = b0 + k <= nb ? a.thr[b0 + k] : INFINITY;
+        __syncthreads();
+
+        const int jstart = !valid ? cnt : j0 > i ? 0 : (int)(i + 1 - j0 < cnt ? i + 1 - j0 : cnt);
+        const int jfirst = __shfl_sync(0xffffffffu, jstart, 0);   // lane 0 starts first
+#pragma unroll 4
+        for (int jj = jfirst; jj < cnt; ++jj) {
+            const double *pj = s_rec + jj * W;
+            double df[D];
+            const double key = vario_key<D, kVarEuclid>(xi, 0.0, pj, df);
+            if (jj >= jstart && key >= th[0] && !(key >= th[K])) {   // in this window (src/variogram.rs:518)
+                // thresholds are sorted: the bin is the number of interior thresholds <= key
+                int idx = 0;
+#pragma unroll
+                for (int k = 1; k < K; ++k) idx += key >= th[k] ? 1 : 0;
+                double e;
+                unsigned int n;
+                if (one_field) {
+                    const double fij = fi - pj[D];
+                    n = fij == fij ? 1u : 0u;            // skip no-data values, src/variogram.rs:524
+                    e = CRESSIE ? __dsqrt_rn(fabs(fij)) : __dmul_rn(fij, fij);
+                    if (!n) e = 0.0;
+                } else {
+                    e = 0.0;
+                    n = 0u;
+                    for (int q = 0; q < a.nf; ++q) {
+                        const double fij = a.f[q * m + i] - a.f[q * m + j0 + jj];
+                        if (fij == fij) {
+                            n += 1u;
+                            e = __dadd_rn(e, CRESSIE ? __dsqrt_rn(fabs(fij)) : __dmul_rn(fij, fij));
+                        }
+                    }
+                }
+                const int s = idx * kVarThreads + tid;
+                w_v[s] = __dadd_rn(w_v[s], e);
+                w_c[s] += n;
+            }
+        }
+        // 128 threads -> one value per window bin, fixed order
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            double vk = w_v[k * kVarThreads + tid];
+            unsigned long long cw = w_c[k * kVarThreads + tid];
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) {
+                vk += __shfl_xor_sync(0xffffffffu, vk, o);
+                cw += __shfl_xor_sync(0xffffffffu, cw, o);
+            }
+            if (lane == 0) {
+                s_wv[warp][k] = vk;
+                s_wc[warp][k] = cw;
+            }
+        }
+        __syncthreads();
+        if (tid < K && b0 + tid < nb) {
+            const double vv = ((s_wv[0][tid] + s_wv[1][tid]) + s_wv[2][tid]) + s_wv[3][tid];
+            const unsigned long long cc = s_wc[0][tid] + s_wc[1][tid] + s_wc[2][tid] + s_wc[3][tid];
+            cta_v[b0 + tid] += vv;
+            cta_c[b0 + tid] += cc;
+        }
+    }
+}
+
 // CTAs -> result, in CTA order.  Pass-local slot (r, b) lands at out[r * nb_total + b0 + b].
 __global__ void gsf_vario_reduce(const double *part_v, const unsigned long long *part_c, int n_parts, int n_dir,
                                  int nb, int nb_total, int b0, double *out_v, unsigned long long *out_c)
