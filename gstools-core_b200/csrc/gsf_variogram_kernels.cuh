@@ -394,46 +394,93 @@ __global__ void gsf_vario_reduce(const double *part_v, const unsigned long long 
     out_c[r * nb_total + b0 + b] = c;
 }
 
-// ---- structured grids: value_k = sum_e est(f[e] - f[e + k*n1]) over the flattened (n0-k, n1) slab ----
+// ---- structured grids: value_k = sum_{i < n0-k, c} est(f[i][c] - f[i+k][c]) ----------------------
+// A CTA owns a block of 32 consecutive lags and walks (64-row x 32-column) tiles of the field: the
+// tile rows i0..i0+64 ("A") and the 96 rows starting at i0 + k0 ("B") sit in shared memory, lane =
+// column, and each of the 8 warps owns 4 consecutive lags.  Going down the rows a thread keeps the
+// 4 B values of its lags in registers and slides that window by one row per step, so a pair costs
+// half a shared-memory load and every field element is fetched from L2 ~13x less often than in a
+// lag-by-lag sweep.  The per-lag sums stay in registers across tiles; lanes are combined by a fixed
+// butterfly at the end and the n_split partial sums per lag are added in order by
+// gsf_vario_struct_reduce: run-to-run deterministic.
 constexpr int kVsThreads = 256;
+constexpr int kVsRows = 64;      // A rows per tile
+constexpr int kVsLags = 32;      // lags per CTA (4 per warp)
+constexpr int kVsCols = 32;      // columns per tile
 
-template <bool MASKED>
+template <bool MASKED, bool CRESSIE>
 __global__ void __launch_bounds__(kVsThreads) gsf_vario_struct(const double *f, const uint8_t *mask, int64_t n0,
-                                                               int64_t n1, int cressie, int n_split,
-                                                               double *part_v, unsigned long long *part_c)
+                                                               int64_t n1, int n_split, double *part_v,
+                                                               unsigned long long *part_c)
 {
-    __shared__ double s_v[kVsThreads / 32];
-    __shared__ unsigned long long s_c[kVsThreads / 32];
-    const int64_t k = (int64_t)blockIdx.x + 1;
-    const int64_t len = (n0 - k) * n1, off = k * n1;
-    // split s owns [s*chunk, (s+1)*chunk), chunk a multiple of the CTA width
-    int64_t chunk = (len + n_split - 1) / n_split;
-    chunk = (chunk + kVsThreads - 1) / kVsThreads * kVsThreads;
-    const int64_t e0 = (int64_t)blockIdx.y * chunk, e1 = e0 + chunk < len ? e0 + chunk : len;
-    double v = 0.0;
-    unsigned long long c = 0ull;
-    for (int64_t e = e0 + threadIdx.x; e < e1; e += kVsThreads) {
-        if (MASKED && (mask[e] || mask[e + off])) continue;   // src/variogram.rs:223-225
-        v = __dadd_rn(v, vario_estimate(cressie, f[e] - f[e + off]));
-        c += 1ull;
+    constexpr int R = kVsRows, KB = kVsLags;
+    __shared__ double sA[R][kVsCols];
+    __shared__ double sB[R + KB][kVsCols];
+    __shared__ uint8_t mA[R][kVsCols];        // 1 = excluded (masked)
+    __shared__ uint8_t mB[R + KB][kVsCols];   // 1 = excluded (masked, or outside the field)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t k0 = 1 + (int64_t)blockIdx.x * KB;   // first lag of this CTA
+    const int wl = 4 * warp;                           // this warp's first lag, relative to k0
+    const int64_t n_rb = (n0 - k0 + R - 1) / R, n_cb = (n1 + kVsCols - 1) / kVsCols;
+    const int64_t n_t = n_rb * n_cb;
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    unsigned long long cn[4] = {0ull, 0ull, 0ull, 0ull};
+
+    auto pair = [&](double a, uint8_t ma, double b, uint8_t mb, int j) {
+        if (!(ma | mb)) {
+            const double d = a - b;
+            v[j] = __dadd_rn(v[j], CRESSIE ? __dsqrt_rn(fabs(d)) : __dmul_rn(d, d));
+            if (MASKED) cn[j] += 1ull;
+        }
+    };
+
+    for (int64_t t = blockIdx.y; t < n_t; t += n_split) {
+        const int64_t i0 = (t / n_cb) * R, col = (t % n_cb) * kVsCols + lane;
+        const bool col_ok = col < n1;
+        __syncthreads();
+        for (int r = warp; r < R + KB; r += kVsThreads / 32) {
+            if (r < R) {
+                const int64_t gi = i0 + r;
+                const bool ok = col_ok && gi < n0;
+                sA[r][lane] = ok ? f[gi * n1 + col] : 0.0;
+                mA[r][lane] = MASKED && ok ? mask[gi * n1 + col] : 0;
+            }
+            const int64_t gi = i0 + k0 + r;
+            const bool ok = col_ok && gi < n0;
+            sB[r][lane] = ok ? f[gi * n1 + col] : 0.0;
+            mB[r][lane] = !ok || (MASKED && mask[gi * n1 + col]) ? 1 : 0;
+        }
+        __syncthreads();
+        double b0 = sB[wl][lane], b1 = sB[wl + 1][lane], b2 = sB[wl + 2][lane], b3;
+        uint8_t q0 = mB[wl][lane], q1 = mB[wl + 1][lane], q2 = mB[wl + 2][lane], q3;
+#pragma unroll 2
+        for (int r = 0; r < R; r += 4) {
+            double a;
+            uint8_t ma;
+            a = sA[r][lane]; ma = MASKED ? mA[r][lane] : 0; b3 = sB[r + wl + 3][lane]; q3 = mB[r + wl + 3][lane];
+            pair(a, ma, b0, q0, 0); pair(a, ma, b1, q1, 1); pair(a, ma, b2, q2, 2); pair(a, ma, b3, q3, 3);
+            a = sA[r + 1][lane]; ma = MASKED ? mA[r + 1][lane] : 0; b0 = sB[r + wl + 4][lane]; q0 = mB[r + wl + 4][lane];
+            pair(a, ma, b1, q1, 0); pair(a, ma, b2, q2, 1); pair(a, ma, b3, q3, 2); pair(a, ma, b0, q0, 3);
+            a = sA[r + 2][lane]; ma = MASKED ? mA[r + 2][lane] : 0; b1 = sB[r + wl + 5][lane]; q1 = mB[r + wl + 5][lane];
+            pair(a, ma, b2, q2, 0); pair(a, ma, b3, q3, 1); pair(a, ma, b0, q0, 2); pair(a, ma, b1, q1, 3);
+            a = sA[r + 3][lane]; ma = MASKED ? mA[r + 3][lane] : 0; b2 = sB[r + wl + 6][lane]; q2 = mB[r + wl + 6][lane];
+            pair(a, ma, b3, q3, 0); pair(a, ma, b0, q0, 1); pair(a, ma, b1, q1, 2); pair(a, ma, b2, q2, 3);
+        }
     }
 #pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) {
-        v += __shfl_xor_sync(0xffffffffu, v, o);
-        c += __shfl_xor_sync(0xffffffffu, c, o);
-    }
-    if ((threadIdx.x & 31) == 0) {
-        s_v[threadIdx.x >> 5] = v;
-        s_c[threadIdx.x >> 5] = c;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int w = 1; w < kVsThreads / 32; ++w) {
-            v += s_v[w];
-            c += s_c[w];
+    for (int j = 0; j < 4; ++j) {
+        double vj = v[j];
+        unsigned long long cj = cn[j];
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            vj += __shfl_xor_sync(0xffffffffu, vj, o);
+            cj += __shfl_xor_sync(0xffffffffu, cj, o);
         }
-        part_v[(size_t)blockIdx.x * n_split + blockIdx.y] = v;
-        part_c[(size_t)blockIdx.x * n_split + blockIdx.y] = c;
+        const int64_t k = k0 + wl + j;
+        if (lane == 0 && k < n0) {
+            part_v[(size_t)(k - 1) * n_split + blockIdx.y] = vj;
+            part_c[(size_t)(k - 1) * n_split + blockIdx.y] = MASKED ? cj : 0ull;
+        }
     }
 }
 
