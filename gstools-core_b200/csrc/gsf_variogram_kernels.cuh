@@ -37,6 +37,19 @@ enum VarioMode { kVarEuclid = 0, kVarHaversine = 1, kVarDirectional = 2 };
 // shared-memory record of one j point: D = 1: (x, f); D = 2: (x, y, f, cos(lat)); D = 3: (x, y, z, f)
 __host__ __device__ constexpr int vario_rec(int d) { return d == 1 ? 2 : 4; }
 
+// dir_test, src/variogram.rs:243-290, for one direction `dr`; df = x_i - x_j, key = |df|^2.
+// The angle test is `|s_prod| / sqrt(key) <= ang_thr` (see above).  Away from the tolerance the
+// sign of s_prod^2 - ang_thr^2 * key decides it without the square root and the division: the
+// computed quotient is within 3e-16 of the real one, the margins a2_lo / a2_hi (ang_thr^2 * (1 -+
+// 1e-13)) are far wider, and only pairs inside that sliver (or with operands near the ends of the
+// double range) take the exact path -- the outcome is the same for every input.
+struct VarioDirTest {
+    int use_bw;            // bandwidth > 0 (src/variogram.rs:262)
+    double bw_thr;         // band distance^2 >= bw_thr  <=>  b_dist >= bandwidth
+    double ang_thr;        // reject when angle <= ang_thr; < 0: the test never rejects
+    double a2_lo, a2_hi;
+};
+
 struct VarioArgs {
     const double *pos;     // [D][m]
     const double *f;       // [nf][m]
@@ -49,9 +62,7 @@ struct VarioArgs {
                            // (thr[0], thr[nb] when monotone, else NaN = filter nothing)
     int n_dir;             // directional only
     const double *dir;     // [n_dir][D]
-    int use_bw;            // bandwidth > 0 (src/variogram.rs:262)
-    double bw_thr;         // band distance^2 >= bw_thr  <=>  b_dist >= bandwidth
-    double ang_thr;        // |s_prod| / dist <= ang_thr  <=>  acos(angle) >= angles_tol
+    VarioDirTest dt;
     int separate;
     int cressie;
     int jc;                // points per j chunk (multiple of 128)
@@ -61,6 +72,33 @@ struct VarioArgs {
     double *part_v;        // [gridDim.x][slots]
     unsigned long long *part_c;
 };
+
+template <int D>
+__device__ __forceinline__ bool vario_dir_pass(const double (&df)[D], const double *dr, double key, const VarioDirTest &p)
+{
+    double s_prod = __dmul_rn(df[0], dr[0]);
+#pragma unroll
+    for (int q = 1; q < D; ++q) s_prod = __dadd_rn(s_prod, __dmul_rn(df[q], dr[q]));
+    if (p.use_bw) {
+        double b2 = 0.0;
+#pragma unroll
+        for (int q = 0; q < D; ++q) {
+            const double w = __dadd_rn(df[q], -__dmul_rn(s_prod, dr[q]));
+            b2 = q == 0 ? __dmul_rn(w, w) : __dadd_rn(b2, __dmul_rn(w, w));
+        }
+        if (b2 >= p.bw_thr) return false;
+    }
+    if (key > 0.0 && p.ang_thr >= 0.0) {
+        const double s2 = s_prod * s_prod;
+        if (key > 1e-280 && key < 1e280 && s2 > 1e-280 && s2 < 1e280) {
+            if (s2 < p.a2_lo * key) return false;
+            if (s2 > p.a2_hi * key) return true;
+        }
+        const double angle = __ddiv_rn(fabs(s_prod), __dsqrt_rn(key));
+        if (angle <= p.ang_thr) return false;
+    }
+    return true;
+}
 
 __device__ __forceinline__ double vario_estimate(int cressie, double d)
 {
@@ -183,25 +221,7 @@ __global__ void __launch_bounds__(kVarThreads) gsf_vario_pairs(VarioArgs a)
                 for (int b = b_lo; b < b_hi; ++b) {
                     if (!searched && (key < s_thr[b] || key >= s_thr[b + 1])) continue;
                     for (int r = 0; r < n_dir; ++r) {
-                        if (MODE == kVarDirectional) {   // dir_test, src/variogram.rs:243-290
-                            const double *dr = s_dir + r * D;
-                            double s_prod = __dmul_rn(df[0], dr[0]);
-#pragma unroll
-                            for (int q = 1; q < D; ++q) s_prod = __dadd_rn(s_prod, __dmul_rn(df[q], dr[q]));
-                            if (a.use_bw) {
-                                double b2 = 0.0;
-#pragma unroll
-                                for (int q = 0; q < D; ++q) {
-                                    const double w = __dadd_rn(df[q], -__dmul_rn(s_prod, dr[q]));
-                                    b2 = q == 0 ? __dmul_rn(w, w) : __dadd_rn(b2, __dmul_rn(w, w));
-                                }
-                                if (b2 >= a.bw_thr) continue;
-                            }
-                            if (key > 0.0) {
-                                const double angle = __ddiv_rn(fabs(s_prod), __dsqrt_rn(key));
-                                if (angle <= a.ang_thr) continue;
-                            }
-                        }
+                        if (MODE == kVarDirectional && !vario_dir_pass<D>(df, s_dir + r * D, key, a.dt)) continue;
                         const int slot = (r * nb + b) * kVarThreads + tid;
                         if (one_field) {
                             const double fij = fi - pj[D];
@@ -256,6 +276,7 @@ __global__ void __launch_bounds__(kVarThreads) gsf_vario_pairs(VarioArgs a)
 // After the tile the 128 threads are combined in a fixed order and added to the CTA's running
 // per-bin totals (global memory, touched once per tile and bin).
 constexpr int kVarWin = 8;
+constexpr int kVarWinDirs = 4;     // most directions the window kernel handles (3 axes + 1)
 
 struct VarioIsoArgs {
     const double *pos;     // [D][m], Morton order
@@ -264,30 +285,37 @@ struct VarioIsoArgs {
     int nf;
     const double *thr;     // [nb + 1], non-decreasing, no NaN
     int nb;
-    int cressie;
     int jc;
     int64_t n_tiles;
     const int3 *tiles;     // (i block, j chunk, first bin of the window)
-    double *part_v;        // [gridDim.x][nb], zeroed by the host
+    // directional only (see VarioArgs)
+    int n_dir;
+    const double *dir;
+    VarioDirTest dt;
+    int separate;
+    double *part_v;        // [gridDim.x][n_dir][nb], zeroed by the host
     unsigned long long *part_c;
 };
 
-template <int D, bool CRESSIE>
+template <int D, bool CRESSIE, bool DIRECTIONAL>
 __global__ void __launch_bounds__(kVarThreads) gsf_vario_iso(VarioIsoArgs a)
 {
-    constexpr int W = vario_rec(D), K = kVarWin;
+    constexpr int W = vario_rec(D), K = kVarWin, MAXS = K * (DIRECTIONAL ? kVarWinDirs : 1);
     extern __shared__ __align__(16) unsigned char vsm[];
+    const int n_dir = DIRECTIONAL ? a.n_dir : 1, slots = n_dir * K;
     double *s_rec = reinterpret_cast<double *>(vsm);                        // [jc][W]
-    double *w_v = s_rec + (size_t)a.jc * W;                                  // [K][128] window sums, one column per thread
-    unsigned int *w_c = reinterpret_cast<unsigned int *>(w_v + K * kVarThreads);   // [K][128]
-    __shared__ double s_wv[kVarThreads / 32][K];
-    __shared__ unsigned long long s_wc[kVarThreads / 32][K];
+    double *w_v = s_rec + (size_t)a.jc * W;                                  // [n_dir][K][128] window sums, one column per thread
+    unsigned int *w_c = reinterpret_cast<unsigned int *>(w_v + slots * kVarThreads);
+    __shared__ double s_wv[kVarThreads / 32][MAXS];
+    __shared__ unsigned long long s_wc[kVarThreads / 32][MAXS];
+    __shared__ double s_dir[DIRECTIONAL ? kVarWinDirs * D : 1];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nb = a.nb, jc = a.jc;
     const int64_t m = a.m;
     const bool one_field = a.nf == 1;
-    double *cta_v = a.part_v + (size_t)blockIdx.x * nb;
-    unsigned long long *cta_c = a.part_c + (size_t)blockIdx.x * nb;
+    double *cta_v = a.part_v + (size_t)blockIdx.x * n_dir * nb;
+    unsigned long long *cta_c = a.part_c + (size_t)blockIdx.x * n_dir * nb;
+    if (DIRECTIONAL && tid < n_dir * D) s_dir[tid] = a.dir[tid];
 
     for (int64_t t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
         const int3 tile = a.tiles[t];
@@ -302,10 +330,9 @@ __global__ void __launch_bounds__(kVarThreads) gsf_vario_iso(VarioIsoArgs a)
             for (int q = 0; q < D; ++q) r[q] = a.pos[q * m + j0 + e];
             r[D] = one_field ? a.f[j0 + e] : 0.0;
         }
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            w_v[k * kVarThreads + tid] = 0.0;
-            w_c[k * kVarThreads + tid] = 0u;
+        for (int s = 0; s < slots; ++s) {
+            w_v[s * kVarThreads + tid] = 0.0;
+            w_c[s * kVarThreads + tid] = 0u;
         }
         const bool valid = i < m;
         double xi[D], fi = 0.0;
@@ -324,7 +351,7 @@ __global__ void __launch_bounds__(kVarThreads) gsf_vario_iso(VarioIsoArgs a)
             const double *pj = s_rec + jj * W;
             double df[D];
             const double key = vario_key<D, kVarEuclid>(xi, 0.0, pj, df);
-            if (jj >= jstart && key >= th[0] && !(key >= th[K])) {   // in this window (src/variogram.rs:518)
+            if (jj >= jstart && key >= th[0] && !(key >= th[K])) {   // in this window (src/variogram.rs:397 / :518)
                 // thresholds are sorted: the bin is the number of interior thresholds <= key
                 int idx = 0;
 #pragma unroll
@@ -333,7 +360,7 @@ __global__ void __launch_bounds__(kVarThreads) gsf_vario_iso(VarioIsoArgs a)
                 unsigned int n;
                 if (one_field) {
                     const double fij = fi - pj[D];
-                    n = fij == fij ? 1u : 0u;            // skip no-data values, src/variogram.rs:524
+                    n = fij == fij ? 1u : 0u;            // skip no-data values, src/variogram.rs:413 / :524
                     e = CRESSIE ? __dsqrt_rn(fabs(fij)) : __dmul_rn(fij, fij);
                     if (!n) e = 0.0;
                 } else {
@@ -347,32 +374,42 @@ __global__ void __launch_bounds__(kVarThreads) gsf_vario_iso(VarioIsoArgs a)
                         }
                     }
                 }
-                const int s = idx * kVarThreads + tid;
-                w_v[s] = __dadd_rn(w_v[s], e);
-                w_c[s] += n;
+                if (!DIRECTIONAL) {
+                    const int s = idx * kVarThreads + tid;
+                    w_v[s] = __dadd_rn(w_v[s], e);
+                    w_c[s] += n;
+                } else {
+                    for (int r = 0; r < n_dir; ++r) {
+                        if (!vario_dir_pass<D>(df, s_dir + r * D, key, a.dt)) continue;
+                        const int s = (r * K + idx) * kVarThreads + tid;
+                        w_v[s] = __dadd_rn(w_v[s], e);
+                        w_c[s] += n;
+                        if (a.separate) break;   // src/variogram.rs:424-426
+                    }
+                }
             }
         }
-        // 128 threads -> one value per window bin, fixed order
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            double vk = w_v[k * kVarThreads + tid];
-            unsigned long long cw = w_c[k * kVarThreads + tid];
+        // 128 threads -> one value per (direction, window bin), fixed order
+        for (int s = 0; s < slots; ++s) {
+            double vk = w_v[s * kVarThreads + tid];
+            unsigned long long cw = w_c[s * kVarThreads + tid];
 #pragma unroll
             for (int o = 16; o >= 1; o >>= 1) {
                 vk += __shfl_xor_sync(0xffffffffu, vk, o);
                 cw += __shfl_xor_sync(0xffffffffu, cw, o);
             }
             if (lane == 0) {
-                s_wv[warp][k] = vk;
-                s_wc[warp][k] = cw;
+                s_wv[warp][s] = vk;
+                s_wc[warp][s] = cw;
             }
         }
         __syncthreads();
-        if (tid < K && b0 + tid < nb) {
+        if (tid < slots && b0 + tid % K < nb) {
             const double vv = ((s_wv[0][tid] + s_wv[1][tid]) + s_wv[2][tid]) + s_wv[3][tid];
             const unsigned long long cc = s_wc[0][tid] + s_wc[1][tid] + s_wc[2][tid] + s_wc[3][tid];
-            cta_v[b0 + tid] += vv;
-            cta_c[b0 + tid] += cc;
+            const int o = (tid / K) * nb + b0 + tid % K;
+            cta_v[o] += vv;
+            cta_c[o] += cc;
         }
     }
 }
