@@ -275,6 +275,9 @@ __global__ void __launch_bounds__(kVarThreads) gsf_vario_pairs(VarioArgs a)
 // kVarWin columns of shared memory, so occupancy no longer depends on the number of bins.
 // After the tile the 128 threads are combined in a fixed order and added to the CTA's running
 // per-bin totals (global memory, touched once per tile and bin).
+struct TrueTag { static constexpr bool value = true; };
+struct FalseTag { static constexpr bool value = false; };
+
 constexpr int kVarWin = 8;
 constexpr int kVarWinDirs = 4;     // most directions the window kernel handles (3 axes + 1)
 
@@ -297,6 +300,36 @@ struct VarioIsoArgs {
     unsigned long long *part_c;
 };
 
+// Shared-memory access through 32-bit shared addresses held in registers: with plain pointers into
+// the dynamic shared array the compiler re-derives the window base (S2UR + 4 uniform instructions)
+// in front of every load of the pair loop.
+__device__ __forceinline__ uint32_t vario_saddr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void vario_lds2(uint32_t addr, double &x, double &y)
+{
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(addr));
+}
+__device__ __forceinline__ double vario_lds1(uint32_t addr)
+{
+    double x;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x) : "r"(addr));
+    return x;
+}
+// one accumulator cell: (sum, count) in 16 bytes
+__device__ __forceinline__ void vario_acc_add(uint32_t addr, double e, unsigned int n)
+{
+    double v;
+    unsigned long long c;
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=d"(v), "=l"(c) : "r"(addr));
+    v = __dadd_rn(v, e);
+    c += n;
+    asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(addr), "d"(v), "l"(c) : "memory");
+}
+// idx += (key >= t): one compare and one predicated add
+__device__ __forceinline__ void vario_count_ge(int &idx, double key, double t)
+{
+    asm("{ .reg .pred p; setp.ge.f64 p, %1, %2; @p add.s32 %0, %0, 1; }" : "+r"(idx) : "d"(key), "d"(t));
+}
+
 template <int D, bool CRESSIE, bool DIRECTIONAL>
 __global__ void __launch_bounds__(kVarThreads) gsf_vario_iso(VarioIsoArgs a)
 {
@@ -304,8 +337,7 @@ __global__ void __launch_bounds__(kVarThreads) gsf_vario_iso(VarioIsoArgs a)
     extern __shared__ __align__(16) unsigned char vsm[];
     const int n_dir = DIRECTIONAL ? a.n_dir : 1, slots = n_dir * K;
     double *s_rec = reinterpret_cast<double *>(vsm);                        // [jc][W]
-    double *w_v = s_rec + (size_t)a.jc * W;                                  // [n_dir][K][128] window sums, one column per thread
-    unsigned int *w_c = reinterpret_cast<unsigned int *>(w_v + slots * kVarThreads);
+    double *w_acc = s_rec + (size_t)a.jc * W;                                // [n_dir][K][128] x (sum, count): one column per thread
     __shared__ double s_wv[kVarThreads / 32][MAXS];
     __shared__ unsigned long long s_wc[kVarThreads / 32][MAXS];
     __shared__ double s_dir[DIRECTIONAL ? kVarWinDirs * D : 1];
@@ -316,6 +348,8 @@ __global__ void __launch_bounds__(kVarThreads) gsf_vario_iso(VarioIsoArgs a)
     double *cta_v = a.part_v + (size_t)blockIdx.x * n_dir * nb;
     unsigned long long *cta_c = a.part_c + (size_t)blockIdx.x * n_dir * nb;
     if (DIRECTIONAL && tid < n_dir * D) s_dir[tid] = a.dir[tid];
+    const uint32_t rec_addr = vario_saddr(s_rec);
+    const uint32_t acc_addr = vario_saddr(w_acc) + tid * 16;   // slot s at acc_addr + s * 2048
 
     for (int64_t t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
         const int3 tile = a.tiles[t];
@@ -331,8 +365,8 @@ __global__ void __launch_bounds__(kVarThreads) gsf_vario_iso(VarioIsoArgs a)
             r[D] = one_field ? a.f[j0 + e] : 0.0;
         }
         for (int s = 0; s < slots; ++s) {
-            w_v[s * kVarThreads + tid] = 0.0;
-            w_c[s * kVarThreads + tid] = 0u;
+            w_acc[(s * kVarThreads + tid) * 2] = 0.0;
+            reinterpret_cast<unsigned long long *>(w_acc)[(s * kVarThreads + tid) * 2 + 1] = 0ull;
         }
         const bool valid = i < m;
         double xi[D], fi = 0.0;
@@ -346,23 +380,39 @@ __global__ void __launch_bounds__(kVarThreads) gsf_vario_iso(VarioIsoArgs a)
 
         const int jstart = !valid ? cnt : j0 > i ? 0 : (int)(i + 1 - j0 < cnt ? i + 1 - j0 : cnt);
         const int jfirst = __shfl_sync(0xffffffffu, jstart, 0);   // lane 0 starts first
+        // the pair loop, specialised on "one field" and on "tile touches the diagonal" (only there
+        // the per-lane start index matters; invalid lanes of the last i block also take that path)
+        auto pair_loop = [&](auto one_tag, auto diag_tag) {
+            constexpr bool ONE = decltype(one_tag)::value, DIAG = decltype(diag_tag)::value;
 #pragma unroll 4
-        for (int jj = jfirst; jj < cnt; ++jj) {
-            const double *pj = s_rec + jj * W;
-            double df[D];
-            const double key = vario_key<D, kVarEuclid>(xi, 0.0, pj, df);
-            if (jj >= jstart && key >= th[0] && !(key >= th[K])) {   // in this window (src/variogram.rs:397 / :518)
+            for (int jj = jfirst; jj < cnt; ++jj) {
+                const uint32_t pj = rec_addr + jj * (W * 8);
+                double rj[4], df[D];
+                vario_lds2(pj, rj[0], rj[1]);                       // D = 1: (x, f); D >= 2: (x, y)
+                if (D == 3) vario_lds2(pj + 16, rj[2], rj[3]);      // (z, f)
+                df[0] = xi[0] - rj[0];
+                double key = __dmul_rn(df[0], df[0]);               // Euclid::dist, src/variogram.rs:93-102
+                if (D >= 2) {
+                    df[D >= 2 ? 1 : 0] = xi[D >= 2 ? 1 : 0] - rj[1];
+                    key = __dadd_rn(key, __dmul_rn(df[D >= 2 ? 1 : 0], df[D >= 2 ? 1 : 0]));
+                }
+                if (D == 3) {
+                    df[D - 1] = xi[D - 1] - rj[2];
+                    key = __dadd_rn(key, __dmul_rn(df[D - 1], df[D - 1]));
+                }
+                if ((DIAG && jj < jstart) || !(key >= th[0]) || key >= th[K]) continue;   // src/variogram.rs:397 / :518
                 // thresholds are sorted: the bin is the number of interior thresholds <= key
                 int idx = 0;
 #pragma unroll
-                for (int k = 1; k < K; ++k) idx += key >= th[k] ? 1 : 0;
+                for (int k = 1; k < K; ++k) vario_count_ge(idx, key, th[k]);
                 double e;
                 unsigned int n;
-                if (one_field) {
-                    const double fij = fi - pj[D];
-                    n = fij == fij ? 1u : 0u;            // skip no-data values, src/variogram.rs:413 / :524
+                if (ONE) {
+                    const double fj = D == 1 ? rj[1] : D == 2 ? vario_lds1(pj + 16) : rj[3];
+                    const double fij = fi - fj;
+                    if (fij != fij) continue;            // skip no-data values, src/variogram.rs:413 / :524
+                    n = 1u;
                     e = CRESSIE ? __dsqrt_rn(fabs(fij)) : __dmul_rn(fij, fij);
-                    if (!n) e = 0.0;
                 } else {
                     e = 0.0;
                     n = 0u;
@@ -375,24 +425,27 @@ __global__ void __launch_bounds__(kVarThreads) gsf_vario_iso(VarioIsoArgs a)
                     }
                 }
                 if (!DIRECTIONAL) {
-                    const int s = idx * kVarThreads + tid;
-                    w_v[s] = __dadd_rn(w_v[s], e);
-                    w_c[s] += n;
+                    vario_acc_add(acc_addr + idx * (kVarThreads * 16), e, n);
                 } else {
                     for (int r = 0; r < n_dir; ++r) {
                         if (!vario_dir_pass<D>(df, s_dir + r * D, key, a.dt)) continue;
-                        const int s = (r * K + idx) * kVarThreads + tid;
-                        w_v[s] = __dadd_rn(w_v[s], e);
-                        w_c[s] += n;
+                        vario_acc_add(acc_addr + (r * K + idx) * (kVarThreads * 16), e, n);
                         if (a.separate) break;   // src/variogram.rs:424-426
                     }
                 }
             }
+        };
+        const bool diag = j0 <= (int64_t)tile.x * kVarThreads + kVarThreads - 1 || (int64_t)(tile.x + 1) * kVarThreads > m;
+        if (one_field) {
+            if (diag) pair_loop(TrueTag(), TrueTag()); else pair_loop(TrueTag(), FalseTag());
+        } else {
+            if (diag) pair_loop(FalseTag(), TrueTag()); else pair_loop(FalseTag(), FalseTag());
         }
+        __syncwarp();
         // 128 threads -> one value per (direction, window bin), fixed order
         for (int s = 0; s < slots; ++s) {
-            double vk = w_v[s * kVarThreads + tid];
-            unsigned long long cw = w_c[s * kVarThreads + tid];
+            double vk = w_acc[(s * kVarThreads + tid) * 2];
+            unsigned long long cw = reinterpret_cast<unsigned long long *>(w_acc)[(s * kVarThreads + tid) * 2 + 1];
 #pragma unroll
             for (int o = 16; o >= 1; o >>= 1) {
                 vk += __shfl_xor_sync(0xffffffffu, vk, o);

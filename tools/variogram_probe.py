@@ -49,18 +49,18 @@ def main():
         rows.append(line)
         print(line, flush=True)
     # directional
-    d, m, nb = 3, 50000, 20
-    pos = rng.uniform(0.0, 1000.0, (d, m))
-    f = rng.normal(size=(1, m))
-    edges = np.linspace(0.0, 300.0, nb + 1)
-    direction = np.eye(3)
-    gc.variogram_directional(f, edges, pos, direction, np.pi / 8, 50.0)
-    t_gpu, _ = best(lambda: gc.variogram_directional(f, edges, pos, direction, np.pi / 8, 50.0))
-    kms = gc.last_stats()["kernel_ms"]
-    line = "| directional d=3 M=%d bins=%d dirs=3 bw=50 | %.2f ms (kernel %.2f ms) | %.1f G pairs/s | - |" % (
-        m, nb, t_gpu * 1e3, kms, m * (m - 1) / 2 / (kms * 1e-3) / 1e9)
-    rows.append(line)
-    print(line, flush=True)
+    for d, m, nb in [(3, 50000, 20), (2, 100000, 20)]:
+        pos = rng.uniform(0.0, 1000.0, (d, m))
+        f = rng.normal(size=(1, m))
+        edges = np.linspace(0.0, 300.0, nb + 1)
+        direction = np.eye(d)
+        gc.variogram_directional(f, edges, pos, direction, np.pi / 8, 50.0)
+        t_gpu, _ = best(lambda: gc.variogram_directional(f, edges, pos, direction, np.pi / 8, 50.0))
+        kms = gc.last_stats()["kernel_ms"]
+        line = "| directional d=%d M=%d bins=%d dirs=%d bw=50 | %.2f ms (kernel %.2f ms) | %.1f G pairs/s | - |" % (
+            d, m, nb, d, t_gpu * 1e3, kms, m * (m - 1) / 2 / (kms * 1e-3) / 1e9)
+        rows.append(line)
+        print(line, flush=True)
     # structured
     for shape, shape_cpu in [((2000, 2000), (500, 2000)), ((8000, 4000), None)]:
         fs = rng.normal(size=shape)
