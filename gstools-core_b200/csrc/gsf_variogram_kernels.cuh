@@ -79,6 +79,16 @@ __device__ __forceinline__ bool vario_dir_pass(const double (&df)[D], const doub
     double s_prod = __dmul_rn(df[0], dr[0]);
 #pragma unroll
     for (int q = 1; q < D; ++q) s_prod = __dadd_rn(s_prod, __dmul_rn(df[q], dr[q]));
+    // Both tests are pure predicates, so the cheap angle decision goes first: it rejects most pairs
+    // (a pi/8 cone holds 8 % of the directions) before the band distance is ever computed.
+    bool angle_known = !(key > 0.0 && p.ang_thr >= 0.0);   // the test does not apply: passes
+    if (!angle_known) {
+        const double s2 = s_prod * s_prod;
+        if (key > 1e-280 && key < 1e280 && s2 > 1e-280 && s2 < 1e280) {
+            if (s2 < p.a2_lo * key) return false;
+            angle_known = s2 > p.a2_hi * key;
+        }
+    }
     if (p.use_bw) {
         double b2 = 0.0;
 #pragma unroll
@@ -88,12 +98,7 @@ __device__ __forceinline__ bool vario_dir_pass(const double (&df)[D], const doub
         }
         if (b2 >= p.bw_thr) return false;
     }
-    if (key > 0.0 && p.ang_thr >= 0.0) {
-        const double s2 = s_prod * s_prod;
-        if (key > 1e-280 && key < 1e280 && s2 > 1e-280 && s2 < 1e280) {
-            if (s2 < p.a2_lo * key) return false;
-            if (s2 > p.a2_hi * key) return true;
-        }
+    if (!angle_known) {
         const double angle = __ddiv_rn(fabs(s_prod), __dsqrt_rn(key));
         if (angle <= p.ang_thr) return false;
     }
@@ -138,6 +143,8 @@ __global__ void __launch_bounds__(kVarThreads) gsf_vario_pairs(VarioArgs a)
     double *s_dir = s_thr + nb + 1;                                                     // [n_dir][D]
     unsigned long long *tot_c = reinterpret_cast<unsigned long long *>(s_dir + n_dir * D);   // [slots]
     unsigned int *acc_c = reinterpret_cast<unsigned int *>(tot_c + slots);              // [slots][128]
+    __shared__ double s_own[kVarThreads][4];              // the CTA's i points: position, field value, cos(lat)
+    __shared__ unsigned int s_q[kVarThreads / 32][64];    // per-warp queue of candidate pairs (lane << 16 | j)
 
     for (int s = 0; s < slots; ++s) {
         acc_v[s * kVarThreads + tid] = 0.0;
@@ -186,10 +193,72 @@ __global__ void __launch_bounds__(kVarThreads) gsf_vario_pairs(VarioArgs a)
         for (int q = 0; q < D; ++q) xi[q] = valid ? a.pos[q * m + i] : 0.0;
         if (valid && one_field) fi = a.f[i];
         if (valid && MODE == kVarHaversine) cos_i = cos(xi[0] * 0.017453292519943295);
+#pragma unroll
+        for (int q = 0; q < D; ++q) s_own[tid][q] = xi[q];
+        s_own[tid][D] = fi;
+        if (MODE == kVarHaversine || D < 3) s_own[tid][3] = cos_i;
         __syncthreads();
+        // One candidate pair: bin it (binary search), test the directions, add it to THIS thread's
+        // accumulator column.  `li` is the warp lane that owns the i point.
+        auto process = [&](unsigned int entry) {
+            const int li = (int)(entry >> 16), jj = (int)(entry & 0xffffu);
+            const double *pi = s_own[warp * 32 + li];
+            const double *pj = s_rec + jj * W;
+            double xo[D], df[D];
+#pragma unroll
+            for (int q = 0; q < D; ++q) xo[q] = pi[q];
+            const double key = vario_key<D, MODE>(xo, pi[3], pj, df);
+            // bins b with !(key < thr[b] || key >= thr[b+1])
+            int b_lo = 0, b_hi = nb;
+            const bool searched = a.monotone && key == key;
+            if (searched) {
+                int lo = 0, hi = nb;   // thr[lo] <= key < thr[hi]
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (s_thr[mid] <= key) lo = mid; else hi = mid;
+                }
+                b_lo = lo;
+                b_hi = lo + 1;
+            }
+            for (int b = b_lo; b < b_hi; ++b) {
+                if (!searched && (key < s_thr[b] || key >= s_thr[b + 1])) continue;
+                for (int r = 0; r < n_dir; ++r) {
+                    if (MODE == kVarDirectional && !vario_dir_pass<D>(df, s_dir + r * D, key, a.dt)) continue;
+                    const int slot = (r * nb + b) * kVarThreads + tid;
+                    if (one_field) {
+                        const double fij = pi[D] - pj[D];
+                        if (fij == fij) {   // skip no-data values, src/variogram.rs:413 / :524
+                            acc_c[slot] += 1u;
+                            acc_v[slot] = __dadd_rn(acc_v[slot], vario_estimate(a.cressie, fij));
+                        }
+                    } else {
+                        const int64_t gi = (int64_t)tile.x * kVarThreads + warp * 32 + li;
+                        double v = acc_v[slot];
+                        unsigned int c = acc_c[slot];
+                        for (int q = 0; q < a.nf; ++q) {
+                            const double fij = a.f[q * m + gi] - a.f[q * m + j0 + jj];
+                            if (fij == fij) {
+                                c += 1u;
+                                v = __dadd_rn(v, vario_estimate(a.cressie, fij));
+                            }
+                        }
+                        acc_v[slot] = v;
+                        acc_c[slot] = c;
+                    }
+                    if (MODE == kVarDirectional && a.separate) break;   // src/variogram.rs:424-426
+                }
+            }
+        };
+
         // only pairs j > i; lanes past the end of the data own no pair
         const int jstart = !valid ? cnt : j0 > i ? 0 : (int)(i + 1 - j0 < cnt ? i + 1 - j0 : cnt);
         const int jb0 = __shfl_sync(0xffffffffu, jstart, 0) / kVarBatch * kVarBatch;   // lane 0 starts first
+        // The range test runs for every (lane, j) with all lanes busy.  The candidates -- a few per
+        // j and warp -- go to a per-warp queue in ballot order (deterministic) and are binned 32 at
+        // a time, again with all lanes busy: the expensive part no longer runs at the lane
+        // utilisation of the hit rate.
+        unsigned int *queue = s_q[warp];
+        int qn = 0;
         for (int jb = jb0; jb < cnt; jb += kVarBatch) {
             unsigned mask = 0u;
 #pragma unroll
@@ -200,53 +269,26 @@ __global__ void __launch_bounds__(kVarThreads) gsf_vario_pairs(VarioArgs a)
                 const bool in = jb + u >= jstart && jb + u < cnt && !(key < pre_lo) && !(key >= pre_hi);
                 mask |= (unsigned)in << u;
             }
-            while (mask) {
-                const int jj = jb + __ffs(mask) - 1;
-                mask &= mask - 1;
-                const double *pj = s_rec + jj * W;
-                double df[D];
-                const double key = vario_key<D, MODE>(xi, cos_i, pj, df);
-                // bins b with !(key < thr[b] || key >= thr[b+1])
-                int b_lo = 0, b_hi = nb;
-                const bool searched = a.monotone && key == key;
-                if (searched) {
-                    int lo = 0, hi = nb;   // thr[lo] <= key < thr[hi]
-                    while (hi - lo > 1) {
-                        const int mid = (lo + hi) >> 1;
-                        if (s_thr[mid] <= key) lo = mid; else hi = mid;
-                    }
-                    b_lo = lo;
-                    b_hi = lo + 1;
-                }
-                for (int b = b_lo; b < b_hi; ++b) {
-                    if (!searched && (key < s_thr[b] || key >= s_thr[b + 1])) continue;
-                    for (int r = 0; r < n_dir; ++r) {
-                        if (MODE == kVarDirectional && !vario_dir_pass<D>(df, s_dir + r * D, key, a.dt)) continue;
-                        const int slot = (r * nb + b) * kVarThreads + tid;
-                        if (one_field) {
-                            const double fij = fi - pj[D];
-                            if (fij == fij) {   // skip no-data values, src/variogram.rs:413 / :524
-                                acc_c[slot] += 1u;
-                                acc_v[slot] = __dadd_rn(acc_v[slot], vario_estimate(a.cressie, fij));
-                            }
-                        } else {
-                            double v = acc_v[slot];
-                            unsigned int c = acc_c[slot];
-                            for (int q = 0; q < a.nf; ++q) {
-                                const double fij = a.f[q * m + i] - a.f[q * m + j0 + jj];
-                                if (fij == fij) {
-                                    c += 1u;
-                                    v = __dadd_rn(v, vario_estimate(a.cressie, fij));
-                                }
-                            }
-                            acc_v[slot] = v;
-                            acc_c[slot] = c;
-                        }
-                        if (MODE == kVarDirectional && a.separate) break;   // src/variogram.rs:424-426
-                    }
+            if (!__any_sync(0xffffffffu, mask != 0u)) continue;
+#pragma unroll 1
+            for (int u = 0; u < kVarBatch; ++u) {
+                const bool in = (mask >> u) & 1u;
+                const unsigned int hits = __ballot_sync(0xffffffffu, in);
+                if (!hits) continue;
+                if (in) queue[qn + __popc(hits & ((1u << lane) - 1u))] = ((unsigned int)lane << 16) | (unsigned int)(jb + u);
+                qn += __popc(hits);
+                if (qn >= 32) {
+                    __syncwarp();
+                    process(queue[lane]);
+                    qn -= 32;
+                    const unsigned int moved = lane < qn ? queue[32 + lane] : 0u;
+                    __syncwarp();
+                    if (lane < qn) queue[lane] = moved;
                 }
             }
         }
+        __syncwarp();
+        if (lane < qn) process(queue[lane]);
         if (++since_flush >= a.flush_every) {
             flush_counts();
             since_flush = 0;
