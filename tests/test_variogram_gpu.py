@@ -286,3 +286,47 @@ def test_field_summation_still_works_after_variograms():
     gc.variogram_unstructured(f2, np.linspace(0, 50, 8), p2)
     gc.variogram_structured(rng.normal(size=(50, 60)))
     assert np.array_equal(before, gc.summate(k, z1, z2, pos))
+
+
+# ---- seeded fuzz over shapes, estimators, edges and directions -----------------------------------
+
+@pytest.mark.parametrize("seed", range(24))
+def test_fuzz_pairs(seed):
+    rng = np.random.default_rng(9000 + seed)
+    d = int(rng.integers(1, 4))
+    m = int(rng.choice([3, 50, 127, 128, 129, 300, 777, 2100]))
+    nf = int(rng.choice([1, 1, 2, 4]))
+    pos, f = scattered(rng, d, m, nf=nf, nan_frac=float(rng.choice([0.0, 0.0, 0.2])))
+    if rng.uniform() < 0.3:
+        pos = np.round(pos / 5.0) * 5.0                     # lattice: repeated points and exact ties
+    nb = int(rng.integers(1, 40))
+    edges = np.sort(rng.uniform(0.0, 120.0, nb + 1))
+    if rng.uniform() < 0.3:
+        edges = np.linspace(0.0, float(rng.uniform(10.0, 150.0)), nb + 1)
+    if rng.uniform() < 0.15:
+        rng.shuffle(edges)                                  # non-monotone: generic kernel, bin-by-bin test
+    est = str(rng.choice(["m", "c"]))
+    if rng.uniform() < 0.5:
+        g, c = gc.variogram_unstructured(f, edges, pos, est, "e")
+        go, co = oracle.variogram_unstructured(f, edges, pos, est, "e", oracle.max_threads())
+    else:
+        nd = int(rng.choice([1, 2, 3, 6]))
+        direction = unit(rng.normal(size=(nd, d)))
+        tol = float(rng.choice([np.pi / 8.0, np.pi / 4.0, 0.2, 1.7]))
+        bw = float(rng.choice([-1.0, 3.0, 20.0]))
+        sep = bool(rng.integers(0, 2))
+        g, c = gc.variogram_directional(f, edges, pos, direction, tol, bw, sep, est)
+        go, co = oracle.variogram_directional(f, edges, pos, direction, tol, bw, sep, est, oracle.max_threads())
+    same_counts(c, co)
+    close(g, go)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_fuzz_structured(seed):
+    rng = np.random.default_rng(9500 + seed)
+    shape = (int(rng.integers(1, 200)), int(rng.integers(1, 150)))
+    f = rng.normal(size=shape)
+    est = str(rng.choice(["m", "c"]))
+    close(gc.variogram_structured(f, est), oracle.variogram_structured(f, est, oracle.max_threads()))
+    mask = rng.uniform(size=shape) < float(rng.uniform(0.0, 0.9))
+    close(gc.variogram_ma_structured(f, mask, est), oracle.variogram_ma_structured(f, mask, est, oracle.max_threads()))

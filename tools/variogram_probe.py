@@ -61,6 +61,18 @@ def main():
             d, m, nb, d, t_gpu * 1e3, kms, m * (m - 1) / 2 / (kms * 1e-3) / 1e9)
         rows.append(line)
         print(line, flush=True)
+    # Haversine (degrees on the unit sphere)
+    m, nb = 50000, 20
+    pos = np.stack([rng.uniform(-80.0, 80.0, m), rng.uniform(-180.0, 180.0, m)])
+    f = rng.normal(size=(1, m))
+    edges = np.linspace(0.0, 1.0, nb + 1)
+    gc.variogram_unstructured(f, edges, pos, "m", "h")
+    t_gpu, _ = best(lambda: gc.variogram_unstructured(f, edges, pos, "m", "h"))
+    kms = gc.last_stats()["kernel_ms"]
+    line = "| unstructured Haversine M=%d bins=%d | %.2f ms (kernel %.2f ms) | %.1f G pairs/s | - |" % (
+        m, nb, t_gpu * 1e3, kms, m * (m - 1) / 2 / (kms * 1e-3) / 1e9)
+    rows.append(line)
+    print(line, flush=True)
     # structured
     for shape, shape_cpu in [((2000, 2000), (500, 2000)), ((8000, 4000), None)]:
         fs = rng.normal(size=shape)
