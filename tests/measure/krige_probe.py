@@ -1,6 +1,6 @@
 """Kriging kernels: time vs the CPU oracle (reference bench shape: 500 conditions x 1e4 points)."""
 import os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "gstools-core_b200")]
 import numpy as np, gstools_core as gc, oracle
 rng = np.random.default_rng(0)

@@ -2,7 +2,7 @@
 kernel-only and end-to-end G point*modes/s, roofline fraction, CPU baseline, structured-grid path,
 and max|delta|/sigma against the oracle on a point subset."""
 import json, os, subprocess, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "gstools-core_b200")]
 import numpy as np
 
@@ -32,7 +32,7 @@ for cfg in ("c1", "c2", "c3", "c4", "c5"):
 
 with open(os.path.join(ROOT, "profiles", "configs_r1.md"), "w") as f:
     f.write("# The five BASELINE.json configs on one B200 (round 1)\n\n")
-    f.write("`python tools/report_configs.py` = `bench.py --workload cN` per config (general point x mode kernel, grid detection off\n"
+    f.write("`python tests/measure/report_configs.py` = `bench.py --workload cN` per config (general point x mode kernel, grid detection off\n"
             "for kernel / e2e / roofline; `grid e2e` = default API behaviour with the structured-grid path) plus a parity check\n"
             "of the full-size result against the CPU oracle on a strided point subset.  G pm/s = 1e9 point*modes per second.\n\n")
     f.write("| cfg | function | d | modes | points | kernel G pm/s | FP64 roofline frac (of measured DFMA peak) | e2e G pm/s (pinned host in/out) | grid-path e2e G pm/s | CPU oracle G pm/s (cores) | e2e / CPU | max abs diff / sigma vs oracle |\n")

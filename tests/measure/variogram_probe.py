@@ -1,12 +1,12 @@
 """Times the variogram estimators on the GPU next to the CPU oracle (bounded oracle sizes: the
-reference algorithm is O(bins * M^2)).  Usage: python tools/variogram_probe.py [out.md]"""
+reference algorithm is O(bins * M^2)).  Usage: python tests/measure/variogram_probe.py [out.md]"""
 import os
 import sys
 import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "gstools-core_b200"))
 import gstools_core as gc  # noqa: E402
