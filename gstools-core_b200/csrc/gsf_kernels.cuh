@@ -42,6 +42,7 @@ constexpr int kThreads = GSF_THREADS;   // threads per CTA (128: measured best o
 constexpr int kTailP = GSF_TAIL_P;  // points per thread of the short tiles that end a launch
 constexpr int kModeBlock = GSF_MODE_BLOCK;   // mode records per shared-memory stage
 constexpr int kStages = 2;
+constexpr int kMaxTemplateDim = 8;   // = GSF_MAX_DIM: gsf_sum_kernel<D,...> is instantiated for D <= 8
 constexpr double kMagic = 6755399441055744.0;  // 1.5 * 2^52
 
 enum Kind : int { kScalar = 0, kIncompr = 1, kFourier = 2 };
@@ -204,6 +205,7 @@ struct SumArgs {
     int64_t n_big;                // number of leading tiles with P points per thread (rest: 1 point)
     double coef[8];               // GSF_U0..U6: kernel parameters live in constant bank 0, which
                                   // DFMA reads as a direct operand (no register, no RF read port)
+    int dim;                      // read by gsf_sum_kernel_anyd only (the templates carry D)
 };
 
 // D: spatial dimension; NC: accumulators per point (1 scalar/fourier, D incompr);
@@ -393,6 +395,29 @@ __global__ void __launch_bounds__(kThreads) gsf_sum_kernel(SumArgs a)
                                                        s_bar);
     }
 #endif
+}
+
+// Scalar / Fourier field in ANY dimension (dim > 8; the reference's ndarray `dot` takes any length,
+// src/field.rs:57).  Completeness path, not a tuned one: one point per thread, the dimension is a
+// run-time loop, mode records and the point's coordinates come through L1 (`__ldg`; a warp reads one
+// record as a broadcast and 32 consecutive points per coordinate row).  Same recipe, same record
+// layout and the same mode order as gsf_sum_kernel<D,1,1,1>.
+__global__ void __launch_bounds__(kThreads) gsf_sum_kernel_anyd(SumArgs a)
+{
+    const int64_t j = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (j >= a.n_points) return;
+    const int D = a.dim;
+    const int R = rec_doubles(D, 1);
+    const PolyCoef coef = {a.coef[0], a.coef[1], a.coef[2], a.coef[3], a.coef[4], a.coef[5], a.coef[6]};
+    const double *x = a.pos + j * a.ps1;
+    double acc = a.offset[0];
+    for (int64_t i = 0; i < a.n_modes; ++i) {
+        const double *m = a.rec + i * R;
+        double t = __ldg(m + D);
+        for (int d = 0; d < D; ++d) t = fma(__ldg(m + d), __ldg(x + d * a.ps0), t);
+        acc = fma(__ldg(m + D + 1), cospi_signed(t, coef), acc);
+    }
+    a.out[j * a.os1] = acc;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -34,8 +34,10 @@ constexpr int kVarBatch = 8;       // j points whose range test runs back to bac
 
 enum VarioMode { kVarEuclid = 0, kVarHaversine = 1, kVarDirectional = 2 };
 
-// shared-memory record of one j point: D = 1: (x, f); D = 2: (x, y, f, cos(lat)); D = 3: (x, y, z, f)
-__host__ __device__ constexpr int vario_rec(int d) { return d == 1 ? 2 : 4; }
+// shared-memory record of one j point: D = 1: (x, f); D = 2: (x, y, f, cos(lat)); D = 3: (x, y, z, f);
+// D >= 4 (generic pair kernel only): (x_0 .. x_{D-1}, f) padded to an even number of doubles
+__host__ __device__ constexpr int vario_rec(int d) { return d == 1 ? 2 : d <= 3 ? 4 : (d + 2) & ~1; }
+constexpr int kVarMaxDim = 8;      // gsf_vario_pairs is instantiated for D = 1..8 (Morton sort / window kernel: D <= 3)
 
 // dir_test, src/variogram.rs:243-290, for one direction `dr`; df = x_i - x_j, key = |df|^2.
 // The angle test is `|s_prod| / sqrt(key) <= ang_thr` (see above).  Away from the tolerance the
@@ -143,7 +145,7 @@ __global__ void __launch_bounds__(kVarThreads) gsf_vario_pairs(VarioArgs a)
     double *s_dir = s_thr + nb + 1;                                                     // [n_dir][D]
     unsigned long long *tot_c = reinterpret_cast<unsigned long long *>(s_dir + n_dir * D);   // [slots]
     unsigned int *acc_c = reinterpret_cast<unsigned int *>(tot_c + slots);              // [slots][128]
-    __shared__ double s_own[kVarThreads][4];              // the CTA's i points: position, field value, cos(lat)
+    __shared__ double s_own[kVarThreads][W < 4 ? 4 : W];  // the CTA's i points: position, field value, cos(lat)
     __shared__ unsigned int s_q[kVarThreads / 32][64];    // per-warp queue of candidate pairs (lane << 16 | j)
 
     for (int s = 0; s < slots; ++s) {

@@ -319,8 +319,10 @@ int validate(const Problem &p)
         if (p.dim != 2 && p.dim != 3)
             return fail(GSF_ERR_DIM, "Only two- and three-dimensional problems are supported. (dim=%d)", p.dim);
         if (p.N == 0) return fail(GSF_ERR_EMPTY_MODES, "summate_incompr needs at least one mode");
-    } else if (p.dim < 1 || p.dim > GSF_MAX_DIM) {
-        return fail(GSF_ERR_DIM, "dim=%d outside the supported range 1..%d", p.dim, GSF_MAX_DIM);
+    } else if (p.dim < 1) {
+        // any dim >= 1 works, as in the reference: 1..GSF_MAX_DIM on the tuned templates, larger
+        // ones on gsf_sum_kernel_anyd
+        return fail(GSF_ERR_DIM, "dim=%d: need at least one spatial dimension", p.dim);
     }
     if (p.N > 0 && (!p.k || !p.z1 || !p.z2 || (p.kind == gsf::kFourier && !p.sf)))
         return fail(GSF_ERR_ARG, "NULL mode array");
@@ -345,6 +347,11 @@ void choose_variant(const DeviceCtx &d, const Problem &p, int64_t m_launch, bool
         return;
     }
     const int64_t ctas1 = (m_launch + kThreads - 1) / kThreads;   // P = 1, L = 1
+    if (p.dim > gsf::kMaxTemplateDim) {   // gsf_sum_kernel_anyd: one point per thread
+        *P = 1;
+        *L = 1;
+        return;
+    }
     if (p.dim > 3) {   // dims 4..8 ship P = 1 and L in {1, 4, 32}
         *P = 1;
         *L = ctas1 >= 2 * d.sm_count ? 1 : (ctas1 * 4 >= 2 * d.sm_count || p.N < 512 ? 4 : 32);
@@ -373,9 +380,12 @@ void choose_variant(const DeviceCtx &d, const Problem &p, int64_t m_launch, bool
 int launch_sum(DeviceCtx &d, const Problem &p, const double *kpos, int64_t ps0, int64_t ps1, double *kout,
                int64_t os0, int64_t os1, int64_t m, cudaStream_t st, int P, int L)
 {
-    SumKernel fn = pick_kernel(p.dim, p.kind == gsf::kIncompr, P, L);
+    const bool anyd = p.dim > gsf::kMaxTemplateDim;
+    if (anyd) { P = 1; L = 1; }
+    SumKernel fn = anyd ? gsf::gsf_sum_kernel_anyd : pick_kernel(p.dim, p.kind == gsf::kIncompr, P, L);
     if (!fn) return fail(GSF_ERR_ARG, "no kernel variant dim=%d P=%d L=%d", p.dim, P, L);
     SumArgs a;
+    a.dim = p.dim;
     a.rec = d.d_rec;
     a.n_modes = p.N;
     a.pos = kpos; a.ps0 = ps0; a.ps1 = ps1;

@@ -40,7 +40,7 @@ extern "C" {
 
 enum gsf_status {
     GSF_OK = 0,
-    GSF_ERR_DIM = 1,        /* dim < 1, dim > GSF_MAX_DIM, or incompr with dim not in {2,3} (field.rs:180) */
+    GSF_ERR_DIM = 1,        /* dim < 1, or incompr with dim not in {2,3} (field.rs:180)                   */
     GSF_ERR_SHAPE = 2,      /* negative sizes / inconsistent arguments (field.rs:44-46 asserts)          */
     GSF_ERR_EMPTY_MODES = 3,/* summator_incompr with 0 modes (reduce_with(..).unwrap(), field.rs:163)    */
     GSF_ERR_NO_DEVICE = 4,  /* no CUDA device / driver; there is no CPU path                             */
@@ -49,6 +49,8 @@ enum gsf_status {
     GSF_ERR_ALLOC = 7       /* host or device allocation failed                                          */
 };
 
+/* Largest dim served by the tuned kernel templates.  Scalar / Fourier calls with a larger dim are
+ * accepted too (the reference takes any dim) and run a plain one-point-per-thread kernel. */
 #define GSF_MAX_DIM 8
 
 /* Per-call statistics of the most recent compute call on this thread's context. Times in ms. */

@@ -67,9 +67,13 @@ def test_shape_mismatch_is_value_error():
 def test_c_abi_validation_codes():
     L = gc._load()
     z = np.ones(3); k = np.ones((9, 3)); pos = np.ones((9, 4)); out = np.zeros(4)
-    rc = L.gsf_summate(9, 3, 4, k.ctypes.data, 3, 1, z.ctypes.data, 1, z.ctypes.data, 1,
+    rc = L.gsf_summate(0, 3, 4, k.ctypes.data, 3, 1, z.ctypes.data, 1, z.ctypes.data, 1,
                        pos.ctypes.data, 4, 1, out.ctypes.data, 0)
     assert rc == 1 and b"dim" in L.gsf_last_error()                       # GSF_ERR_DIM
+    if gc.device_count() == 0:   # dim = 9 passes validation (any dim works, as in the reference)
+        rc = L.gsf_summate(9, 3, 4, k.ctypes.data, 3, 1, z.ctypes.data, 1, z.ctypes.data, 1,
+                           pos.ctypes.data, 4, 1, out.ctypes.data, 0)
+        assert rc == 4                                                     # GSF_ERR_NO_DEVICE
     rc = L.gsf_summate_incompr(1, 3, 4, k.ctypes.data, 3, 1, z.ctypes.data, 1, z.ctypes.data, 1,
                                pos.ctypes.data, 4, 1, out.ctypes.data, 1, 1, 0)
     assert rc == 1 and b"two- and three-dimensional" in L.gsf_last_error()  # field.rs:180

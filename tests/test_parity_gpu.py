@@ -69,7 +69,7 @@ def _rand(seed, d, n, m, heavy=False, span=50.0):
     return k, z1, z2, pos
 
 
-@pytest.mark.parametrize("d", [1, 2, 3, 4, 5, 8])
+@pytest.mark.parametrize("d", [1, 2, 3, 4, 5, 8, 9, 17])     # d > 8: gsf_sum_kernel_anyd (any dim, like the reference)
 @pytest.mark.parametrize("n,m", [(1, 1), (10, 8), (257, 1031), (1000, 4099)])
 def test_summate_random(d, n, m):
     k, z1, z2, pos = _rand(100 + d, d, n, m, heavy=(d == 3))
@@ -77,6 +77,24 @@ def test_summate_random(d, n, m):
     got = gc.summate(k, z1, z2, pos)
     assert got.shape == ref.shape
     assert rel_err(got, ref) <= TOL
+
+
+def test_any_dim_strided_scaled_and_chunked():
+    """dim > 8 through every host route: strided views, forced chunks, fused scale/offset"""
+    d, n, m = 12, 130, 70001
+    k, z1, z2, pos = _rand(77, d, n, m)
+    ref = oracle.summate(k, z1, z2, pos)
+    big = np.zeros((d, 2 * m))
+    big[:, ::2] = pos
+    assert rel_err(gc.summate(k, z1, z2, big[:, ::2]), ref) <= TOL          # strided pos
+    gc.set_chunk_points(8192)
+    try:
+        got = gc.summate(k, z1, z2, pos)
+    finally:
+        gc.set_chunk_points(0)
+    assert rel_err(got, ref) <= TOL
+    got = gc.summate_scaled(k, z1, z2, pos, scale=0.25, offset=3.0)
+    assert rel_err(got, 0.25 * ref + 3.0) <= TOL
 
 
 @pytest.mark.parametrize("d", [2, 3])
@@ -89,7 +107,7 @@ def test_incompr_random(d, n, m):
     assert rel_err(got, ref) <= TOL
 
 
-@pytest.mark.parametrize("d", [1, 2, 3])
+@pytest.mark.parametrize("d", [1, 2, 3, 11])
 def test_fourier_random(d):
     k, z1, z2, pos = _rand(300 + d, d, 513, 2050)
     sf = np.random.default_rng(9).normal(size=513)            # the reference's KAT uses signed factors

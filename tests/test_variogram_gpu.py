@@ -78,17 +78,31 @@ def test_kat_unstructured_and_directional(vkat):
 
 # ---- unstructured --------------------------------------------------------------------------------
 
-@pytest.mark.parametrize("d", [1, 2, 3])
+@pytest.mark.parametrize("d", [1, 2, 3, 4, 5, 8])      # d >= 4: generic pair kernel, points in input order
 @pytest.mark.parametrize("est", ["m", "c"])
 @pytest.mark.parametrize("m", [1, 2, 129, 1500])
 def test_unstructured_random(d, est, m):
     rng = np.random.default_rng(100 * d + m)
     pos, f = scattered(rng, d, m)
-    edges = np.linspace(0.0, 60.0, 17)
+    edges = np.linspace(0.0, 60.0 * max(1.0, np.sqrt(d / 3.0)), 17)   # typical distances grow like sqrt(d)
     g, c = gc.variogram_unstructured(f, edges, pos, est, "e")
     go, co = oracle.variogram_unstructured(f, edges, pos, est, "e", oracle.max_threads())
     same_counts(c, co)
     close(g, go)
+
+
+def test_space_time_lattice_ties_and_dim_limit():
+    """4-D integer lattice (exact ties at the bin edges, several j chunks); dim 9 is refused loudly"""
+    rng = np.random.default_rng(44)
+    pos = rng.integers(0, 6, size=(4, 2500)).astype(np.float64)
+    f = rng.normal(size=(1, 2500))
+    edges = np.arange(0.0, 9.0)
+    g, c = gc.variogram_unstructured(f, edges, pos, "m", "e")
+    go, co = oracle.variogram_unstructured(f, edges, pos, "m", "e", oracle.max_threads())
+    same_counts(c, co)
+    close(g, go)
+    with pytest.raises(ValueError):
+        gc.variogram_unstructured(f[:, :10], edges, rng.normal(size=(9, 10)), "m", "e")
 
 
 def test_unstructured_integer_lattice_ties():
@@ -194,13 +208,13 @@ def unit(v):
     return v / np.linalg.norm(v, axis=1, keepdims=True)
 
 
-@pytest.mark.parametrize("d", [1, 2, 3])
+@pytest.mark.parametrize("d", [1, 2, 3, 4, 6, 7])
 @pytest.mark.parametrize("bandwidth,separate", [(-1.0, False), (8.0, False), (8.0, True), (-1.0, True)])
 def test_directional_random(d, bandwidth, separate):
     rng = np.random.default_rng(200 + d)
     pos, f = scattered(rng, d, 900, nf=2, nan_frac=0.05)
     direction = unit(rng.normal(size=(3, d)))
-    edges = np.linspace(0.0, 50.0, 11)
+    edges = np.linspace(0.0, 50.0 * max(1.0, np.sqrt(d / 3.0)), 11)
     for est in ("m", "c"):
         g, c = gc.variogram_directional(f, edges, pos, direction, np.pi / 6.0, bandwidth, separate, est)
         go, co = oracle.variogram_directional(f, edges, pos, direction, np.pi / 6.0, bandwidth, separate, est,
