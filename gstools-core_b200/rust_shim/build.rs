@@ -29,7 +29,8 @@ fn main() {
     println!("cargo:rustc-link-lib=dylib=dl");
     println!("cargo:rustc-link-lib=dylib=rt");
     println!("cargo:rustc-link-lib=dylib=pthread");
-    for f in ["gsfield.cu", "gsf_kernels.cuh", "cospi_poly.cuh"] {
-        println!("cargo:rerun-if-changed={}", csrc.join(f).display());
-    }
+    // gsfield.cu includes every .cuh / .inc next to it: watch the whole directory
+    println!("cargo:rerun-if-changed={}", csrc.display());
+    println!("cargo:rerun-if-env-changed=NVCC");
+    println!("cargo:rerun-if-env-changed=GSFIELD_CSRC");
 }
