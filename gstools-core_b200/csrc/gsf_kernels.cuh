@@ -47,6 +47,30 @@ constexpr double kMagic = 6755399441055744.0;  // 1.5 * 2^52
 
 enum Kind : int { kScalar = 0, kIncompr = 1, kFourier = 2 };
 
+// Polynomial form of the hot loop (cospi_poly.cuh):
+//   0: u = U(s) by 6 DFMA, y = u*u - 1.  The first Horner step fma(U6, s, U5) has TWO constant
+//      operands; a DFMA takes at most one from the constant bank / a uniform register, so ptxas
+//      keeps both in registers: three register-file reads = 3 issue cycles instead of 2.
+//   1: U = c*Q with Q monic: v = s + Q5 (DADD), 5 DFMA, w = v*v - 1/c^2; the factor c^2 is folded
+//      into the mode amplitudes by gsf_prep_modes.  Same FP64 instruction count, no instruction
+//      with three register sources in the polynomial.
+#ifndef GSF_POLY_MONIC
+#define GSF_POLY_MONIC 1
+#endif
+constexpr bool kPolyMonic = GSF_POLY_MONIC != 0;
+// amplitude factor the pre-pass folds into the records of the point x mode kernels
+constexpr double kAmpFactor = kPolyMonic ? GSF_QS : 1.0;
+// the 7 constants handed to the kernels as SumArgs::coef (c0..c5: Horner constants, c6: see cospi_signed)
+__host__ __device__ inline void poly_constants(double *c)
+{
+    if (kPolyMonic) {
+        c[0] = GSF_Q0; c[1] = GSF_Q1; c[2] = GSF_Q2; c[3] = GSF_Q3; c[4] = GSF_Q4; c[5] = GSF_Q5; c[6] = -(GSF_QE);
+    } else {
+        c[0] = GSF_U0; c[1] = GSF_U1; c[2] = GSF_U2; c[3] = GSF_U3; c[4] = GSF_U4; c[5] = GSF_U5; c[6] = GSF_U6;
+    }
+    c[7] = 0.0;
+}
+
 // doubles per pre-processed mode record: kh[D], th, A[NC], padded to an even count so every
 // record (and every block of records) is a multiple of 16 bytes (TMA bulk-copy granularity).
 __host__ __device__ constexpr int rec_doubles(int D, int NC) { return (D + 1 + NC + 1) & ~1; }
@@ -157,21 +181,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 }
 
 // ------------------------------------------------------------------------------------------
-// The seven polynomial coefficients live in constant memory and are read ONCE per thread into
-// registers: as literals ptxas re-materialises them with UMOV pairs inside the mode loop, and
-// every non-FP64 instruction there costs an issue cycle the FP64 pipe could have used.
+// The seven polynomial constants travel as kernel parameters (SumArgs::coef, constant bank 0): as
+// literals ptxas re-materialises them with UMOV pairs inside the mode loop, and every non-FP64
+// instruction there costs an issue cycle the FP64 pipe could have used.
 struct PolyCoef {
     double c0, c1, c2, c3, c4, c5, c6;
 };
-__constant__ double gsf_poly_u[8] = {GSF_U0, GSF_U1, GSF_U2, GSF_U3, GSF_U4, GSF_U5, GSF_U6, 0.0};
-__device__ __forceinline__ PolyCoef load_coef()
-{
-    PolyCoef c;
-    c.c0 = gsf_poly_u[0]; c.c1 = gsf_poly_u[1]; c.c2 = gsf_poly_u[2]; c.c3 = gsf_poly_u[3];
-    c.c4 = gsf_poly_u[4]; c.c5 = gsf_poly_u[5]; c.c6 = gsf_poly_u[6];
-    return c;
-}
-
 // (-1)^rint(t) * cos(pi*r): cos(pi*t) for the reduced argument with the sign applied.
 // 11 FP64-pipe instructions + 1 integer multiply-add: adding parity<<31 to the high word
 // modulo 2^32 is exactly an XOR of the sign bit.
@@ -181,13 +196,13 @@ __device__ __forceinline__ double cospi_signed(double t, const PolyCoef &c)
     const double nf = __dadd_rn(tn, -kMagic);   // rint(t) as a double
     const double r = __dadd_rn(t, -nf);         // exact, |r| <= 1/2
     const double s = __dmul_rn(r, r);
-    double u = fma(c.c6, s, c.c5);
+    double u = kPolyMonic ? __dadd_rn(s, c.c5) : fma(c.c6, s, c.c5);
     u = fma(u, s, c.c4);
     u = fma(u, s, c.c3);
     u = fma(u, s, c.c2);
     u = fma(u, s, c.c1);
     u = fma(u, s, c.c0);
-    const double y = fma(u, u, -1.0);
+    const double y = kPolyMonic ? fma(u, u, c.c6) : fma(u, u, -1.0);   // monic: c6 = -1/c^2
     const uint32_t hi = static_cast<uint32_t>(__double2hiint(y)) +
                         (static_cast<uint32_t>(__double2loint(tn)) << 31);
     return __hiloint2double(static_cast<int>(hi), __double2loint(y));
@@ -218,7 +233,7 @@ struct SumArgs {
 template <int D, int NC, int P>
 __host__ __device__ constexpr int gsf_style() { return 1; }
 template <int D, int NC, int P>
-__host__ __device__ constexpr int gsf_unroll() { return (D == 3 && NC == 1 && P == 3) ? 4 : 8; }
+__host__ __device__ constexpr int gsf_unroll() { return (D == 2 && NC == 1 && P == 3) ? 4 : 8; }   // re-measured with the monic polynomial
 #else
 template <int D, int NC, int P>
 __host__ __device__ constexpr int gsf_style() { return GSF_TUNE_STYLE; }
@@ -328,7 +343,7 @@ __device__ __forceinline__ void sum_tile(const SumArgs &a, const int64_t tile0,
                 sq[p] = __dmul_rn(r, r);
             }
 #pragma unroll
-            for (int p = 0; p < P; ++p) u[p] = fma(coef.c6, sq[p], coef.c5);
+            for (int p = 0; p < P; ++p) u[p] = kPolyMonic ? __dadd_rn(sq[p], coef.c5) : fma(coef.c6, sq[p], coef.c5);
 #pragma unroll
             for (int p = 0; p < P; ++p) u[p] = fma(u[p], sq[p], coef.c4);
 #pragma unroll
@@ -341,7 +356,8 @@ __device__ __forceinline__ void sum_tile(const SumArgs &a, const int64_t tile0,
             for (int p = 0; p < P; ++p) u[p] = fma(u[p], sq[p], coef.c0);
 #pragma unroll
             for (int p = 0; p < P; ++p) {
-                const double y = fma(u[p], u[p], -1.0);                         // cos(pi r)
+                const double y = kPolyMonic ? fma(u[p], u[p], coef.c6)           // cos(pi r) / c^2
+                                            : fma(u[p], u[p], -1.0);             // cos(pi r)
                 const uint32_t hi = static_cast<uint32_t>(__double2hiint(y)) +
                                     (static_cast<uint32_t>(__double2loint(tn[p])) << 31);
                 u[p] = __hiloint2double(static_cast<int>(hi), __double2loint(y));   // (-1)^n cos(pi r)

@@ -392,10 +392,7 @@ int launch_sum(DeviceCtx &d, const Problem &p, const double *kpos, int64_t ps0, 
     a.n_points = m;
     a.out = kout; a.os0 = os0; a.os1 = os1;
     for (int c = 0; c < 3; ++c) a.offset[c] = p.offset[c];
-    {
-        static const double u[8] = {GSF_U0, GSF_U1, GSF_U2, GSF_U3, GSF_U4, GSF_U5, GSF_U6, 0.0};
-        for (int c = 0; c < 8; ++c) a.coef[c] = u[c];
-    }
+    gsf::poly_constants(a.coef);
     // long tiles (P points per thread) first, then short tiles (1 point per thread) for the last
     // `tail` resident waves so that the machine drains in small steps (see gsf_sum_kernel)
     const int64_t tile = (int64_t)P * (kThreads / L);
@@ -437,9 +434,12 @@ int launch_sum(DeviceCtx &d, const Problem &p, const double *kpos, int64_t ps0, 
 
 // Upload (if host) and pre-process the modes on `st`.  Host arrays are gathered into a contiguous
 // temporary and copied with a pageable cudaMemcpyAsync (staged by the driver before it returns).
-int prepare_modes(DeviceCtx &d, const Problem &p, cudaStream_t st)
+// `amp_factor`: what the consumer of the records wants folded into the amplitudes besides p.scale
+// (gsf::kAmpFactor for the point x mode kernels, 1 for the structured-grid tables).
+int prepare_modes(DeviceCtx &d, const Problem &p, cudaStream_t st, double amp_factor = gsf::kAmpFactor)
 {
     const int64_t N = p.N;
+    const double scale = amp_factor == 1.0 ? p.scale : p.scale * amp_factor;
     int rc;
     {
         const size_t cap_before = d.rec_cap;
@@ -462,7 +462,7 @@ int prepare_modes(DeviceCtx &d, const Problem &p, cudaStream_t st)
     a.n_modes = N;
     a.dim = p.dim;
     a.incompr = p.kind == gsf::kIncompr;
-    a.scale = p.scale;
+    a.scale = scale;
     a.rec = d.d_rec;
     if (all_dev) {
         if (kd != d.dev && kd != p.peer_owner)
@@ -483,11 +483,11 @@ int prepare_modes(DeviceCtx &d, const Problem &p, cudaStream_t st)
         for (int64_t i = 0; i < N; ++i) h[(size_t)(p.dim + 1) * N + i] = p.z2[i * p.z2s];
         if (p.kind == gsf::kFourier)
             for (int64_t i = 0; i < N; ++i) h[(size_t)(p.dim + 2) * N + i] = p.sf[i * p.sfs];
-        if (d.rec_valid && d.rec_kind == p.kind && d.rec_dim == p.dim && d.rec_n == N && d.rec_scale == p.scale &&
+        if (d.rec_valid && d.rec_kind == p.kind && d.rec_dim == p.dim && d.rec_n == N && d.rec_scale == scale &&
             d.rec_src.size() == h.size() && memcmp(d.rec_src.data(), h.data(), h.size() * sizeof(double)) == 0)
             return GSF_OK;   // d_rec already holds exactly these modes
         d.rec_src = h;
-        d.rec_kind = p.kind; d.rec_dim = p.dim; d.rec_n = N; d.rec_scale = p.scale;
+        d.rec_kind = p.kind; d.rec_dim = p.dim; d.rec_n = N; d.rec_scale = scale;
         d.rec_valid = true;
         GSF_CUDA(cudaMemcpyAsync(d.d_raw, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, st));
         d.h2d_bytes += (int64_t)(h.size() * sizeof(double));

@@ -105,8 +105,7 @@ double run(int64_t m, int n_modes)
     cudaMemcpy(dpos, pos.data(), pos.size() * 8, cudaMemcpyHostToDevice);
     SumArgs a{};
     a.n_modes = n_modes; a.pos = dpos; a.ps0 = m; a.ps1 = 1; a.n_points = m; a.out = dout; a.os0 = 1; a.os1 = NC;
-    const double u[8] = {GSF_U0, GSF_U1, GSF_U2, GSF_U3, GSF_U4, GSF_U5, GSF_U6, 0};
-    for (int c = 0; c < 8; ++c) a.coef[c] = u[c];
+    gsf::poly_constants(a.coef);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     float best = 1e9f;
     const int64_t grid = (m + 128 * P - 1) / (128 * P);

@@ -27,8 +27,7 @@ double run(int64_t m, int n_modes, double tail_waves)
     SumArgs a{};
     a.rec = drec; a.n_modes = n_modes; a.pos = dpos; a.ps0 = m; a.ps1 = 1; a.n_points = m;
     a.out = dout; a.os0 = 1; a.os1 = NC;
-    const double u[8] = {GSF_U0, GSF_U1, GSF_U2, GSF_U3, GSF_U4, GSF_U5, GSF_U6, 0};
-    for (int c = 0; c < 8; ++c) a.coef[c] = u[c];
+    gsf::poly_constants(a.coef);
     const int64_t tile = (int64_t)P * kThreads;
     int64_t tail_pts = (int64_t)(tail_waves * 148 * 8 * (double)tile);
     if (tail_pts > m) tail_pts = m;
@@ -50,7 +49,7 @@ double run(int64_t m, int n_modes, double tail_waves)
 
 int main()
 {
-    printf("style=%d unroll=%d |", GSF_TUNE_STYLE, GSF_TUNE_UNROLL);
+    printf("monic=%d style=%d unroll=%d |", GSF_POLY_MONIC, GSF_TUNE_STYLE, GSF_TUNE_UNROLL);
     printf(" d3s P3 1M %.0f 4M %.0f |", run<3, 1, 3>(1000000, 1000, 0.5), run<3, 1, 3>(4000000, 1000, 0.5));
     printf(" d3s P4 4M %.0f | d3s P2 4M %.0f |", run<3, 1, 4>(4000000, 1000, 0.5), run<3, 1, 2>(4000000, 1000, 0.5));
     printf(" d3i P3 1M %.0f 4M %.0f | d3i P2 4M %.0f |", run<3, 3, 3>(1000000, 1000, 0.5), run<3, 3, 3>(4000000, 1000, 0.5), run<3, 3, 2>(4000000, 1000, 0.5));

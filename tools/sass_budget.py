@@ -1,0 +1,121 @@
+#!/usr/bin/env python3
+"""Static issue-slot budget of the mode loop of gsf_sum_kernel<D,NC,P,1>, from SASS.
+
+Usage:  python tools/sass_budget.py <binary or .so> [D NC P]       (default 3 1 3)
+
+Finds the hottest innermost loop of the kernel (the one holding the most FP64 instructions)
+and prices its body with the issue model measured on B200 (tools/micro/dfma_patterns.cu):
+
+  * an FP64 instruction (DFMA / DADD / DMUL) holds the SMSP issue port for 2 cycles, everything
+    else for 1;
+  * an FP64 instruction that reads THREE distinct general registers from the register file costs
+    a third cycle.  A source is free when it is a constant / uniform / immediate operand, repeats
+    another source of the same instruction, or is served by the operand-reuse cache (the previous
+    FP64 instruction carried the same register in the same slot with `.reuse`).
+
+Prints the instruction mix, the penalty count and the predicted FP64-pipe utilisation
+(2 * #FP64 / cycles) -- a way to compare schedule variants without a GPU.  The model reproduces
+the ncu figure of the shipped kernel within about two points (87.8 % measured at C2)."""
+import re
+import subprocess
+import sys
+
+
+def kernel_sass(path, d, nc, p):
+    out = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True, check=True).stdout
+    name = "_ZN3gsf14gsf_sum_kernelILi%dELi%dELi%dELi1EEEvNS_7SumArgsE" % (d, nc, p)
+    lines, on = [], False
+    for ln in out.splitlines():
+        if "Function :" in ln:
+            on = name in ln
+            continue
+        if on:
+            m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(.*?);", ln)
+            if m:
+                lines.append((int(m.group(1), 16), m.group(2).strip()))
+    if not lines:
+        raise SystemExit("kernel %s not found in %s" % (name, path))
+    return lines
+
+
+FP64 = ("DFMA", "DADD", "DMUL")
+
+
+def opcode(text):
+    t = text.split()
+    return (t[1] if t[0].startswith("@") else t[0]).split(".")[0]
+
+
+def hottest_loop(lines):
+    addr_index = {a: i for i, (a, _) in enumerate(lines)}
+    best = None
+    for i, (a, text) in enumerate(lines):
+        if opcode(text) != "BRA":
+            continue
+        m = re.search(r"0x([0-9a-f]+)", text)
+        if not m:
+            continue
+        tgt = int(m.group(1), 16)
+        if tgt >= a or tgt not in addr_index:
+            continue
+        body = lines[addr_index[tgt]:i + 1]
+        # innermost loops only: no other backward branch inside the body
+        inner = False
+        for a2, t2 in body[:-1]:
+            if opcode(t2) == "BRA":
+                m2 = re.search(r"0x([0-9a-f]+)", t2)
+                if m2 and int(m2.group(1), 16) <= a2:
+                    inner = True
+        if inner:
+            continue
+        n64 = sum(opcode(t) in FP64 for _, t in body)
+        if best is None or n64 > best[0]:
+            best = (n64, body)
+    return best[1]
+
+
+def sources(text):
+    """register sources of an FP64 instruction as (name, reuse) per slot, None for non-register operands"""
+    ops = text.split(None, 1)[1] if not text.startswith("@") else text.split(None, 2)[2]
+    parts = [x.strip() for x in ops.split(",")][1:]   # drop the destination
+    res = []
+    for x in parts:
+        m = re.match(r"^-?\|?(R\d+)\|?(\.reuse)?$", x)
+        res.append((m.group(1), bool(m.group(2))) if m and m.group(1) != "RZ" else None)
+    return res
+
+
+def main():
+    path = sys.argv[1]
+    d, nc, p = (int(x) for x in sys.argv[2:5]) if len(sys.argv) >= 5 else (3, 1, 3)
+    body = hottest_loop(kernel_sass(path, d, nc, p))
+    mix = {}
+    prev = None
+    penalties = 0
+    for _, text in body:
+        op = opcode(text)
+        mix[op] = mix.get(op, 0) + 1
+        if op in FP64:
+            src = sources(text)
+            fresh = set()
+            for slot, s in enumerate(src):
+                if s is None:
+                    continue
+                cached = prev is not None and slot < len(prev) and prev[slot] is not None \
+                    and prev[slot][0] == s[0] and prev[slot][1]
+                if not cached:
+                    fresh.add(s[0])
+            if len(fresh) >= 3:
+                penalties += 1
+            prev = src
+    n64 = sum(v for k, v in mix.items() if k in FP64)
+    other = sum(v for k, v in mix.items() if k not in FP64)
+    cycles = 2 * n64 + other + penalties
+    print("%s  <D=%d NC=%d P=%d>  loop body: %d instructions" % (path, d, nc, p, len(body)))
+    print("  mix: " + ", ".join("%s %d" % kv for kv in sorted(mix.items(), key=lambda kv: -kv[1])))
+    print("  FP64 %d (x2 cycles)  other %d  three-register FP64 %d  => %d cycles, FP64 pipe %.1f %%"
+          % (n64, other, penalties, cycles, 200.0 * n64 / cycles))
+
+
+if __name__ == "__main__":
+    main()
