@@ -21,8 +21,35 @@ import subprocess
 import sys
 
 
+_DUMPS = {}
+
+
+def sass_dump(path):
+    """`cuobjdump -sass` of a binary / shared library (cached per path)"""
+    if path not in _DUMPS:
+        _DUMPS[path] = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True, check=True).stdout
+    return _DUMPS[path]
+
+
+def function_sass(path, mangled_substring):
+    """[(address, instruction text)] of the first function whose mangled name contains the substring"""
+    lines, on, seen = [], False, False
+    for ln in sass_dump(path).splitlines():
+        if "Function :" in ln:
+            if seen and on:
+                break
+            on = mangled_substring in ln
+            seen = seen or on
+            continue
+        if on:
+            m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(.*?);", ln)
+            if m:
+                lines.append((int(m.group(1), 16), m.group(2).strip()))
+    return lines
+
+
 def kernel_sass(path, d, nc, p):
-    out = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True, check=True).stdout
+    out = sass_dump(path)
     name = "_ZN3gsf14gsf_sum_kernelILi%dELi%dELi%dELi1EEEvNS_7SumArgsE" % (d, nc, p)
     lines, on = [], False
     for ln in out.splitlines():
@@ -85,9 +112,8 @@ def sources(text):
     return res
 
 
-def main():
-    path = sys.argv[1]
-    d, nc, p = (int(x) for x in sys.argv[2:5]) if len(sys.argv) >= 5 else (3, 1, 3)
+def analyze(path, d=3, nc=1, p=3):
+    """issue budget of the mode loop: dict(mix, fp64, other, three_register, cycles, pipe_frac, body_len)"""
     body = hottest_loop(kernel_sass(path, d, nc, p))
     mix = {}
     prev = None
@@ -111,10 +137,18 @@ def main():
     n64 = sum(v for k, v in mix.items() if k in FP64)
     other = sum(v for k, v in mix.items() if k not in FP64)
     cycles = 2 * n64 + other + penalties
-    print("%s  <D=%d NC=%d P=%d>  loop body: %d instructions" % (path, d, nc, p, len(body)))
-    print("  mix: " + ", ".join("%s %d" % kv for kv in sorted(mix.items(), key=lambda kv: -kv[1])))
+    return {"mix": mix, "fp64": n64, "other": other, "three_register": penalties, "cycles": cycles,
+            "pipe_frac": 2.0 * n64 / cycles, "body_len": len(body)}
+
+
+def main():
+    path = sys.argv[1]
+    d, nc, p = (int(x) for x in sys.argv[2:5]) if len(sys.argv) >= 5 else (3, 1, 3)
+    r = analyze(path, d, nc, p)
+    print("%s  <D=%d NC=%d P=%d>  loop body: %d instructions" % (path, d, nc, p, r["body_len"]))
+    print("  mix: " + ", ".join("%s %d" % kv for kv in sorted(r["mix"].items(), key=lambda kv: -kv[1])))
     print("  FP64 %d (x2 cycles)  other %d  three-register FP64 %d  => %d cycles, FP64 pipe %.1f %%"
-          % (n64, other, penalties, cycles, 200.0 * n64 / cycles))
+          % (r["fp64"], r["other"], r["three_register"], r["cycles"], 100.0 * r["pipe_frac"]))
 
 
 if __name__ == "__main__":
