@@ -2,6 +2,8 @@
 """Static issue-slot budget of the mode loop of gsf_sum_kernel<D,NC,P,1>, from SASS.
 
 Usage:  python tools/sass_budget.py <binary or .so> [D NC P]       (default 3 1 3)
+        python tools/sass_budget.py <binary or .so> --kernel <mangled-name substring>
+                                                    (instruction mix of any kernel's hottest loop)
 
 Finds the hottest innermost loop of the kernel (the one holding the most FP64 instructions)
 and prices its body with the issue model measured on B200 (tools/micro/dfma_patterns.cu):
@@ -141,8 +143,42 @@ def analyze(path, d=3, nc=1, p=3):
             "pipe_frac": 2.0 * n64 / cycles, "body_len": len(body)}
 
 
+def loop_mix(path, mangled_substring, hot=("DMMA",) + FP64):
+    """instruction mix of the innermost loop of any kernel that holds the most `hot` instructions"""
+    lines = function_sass(path, mangled_substring)
+    if not lines:
+        raise SystemExit("no function matching %s in %s" % (mangled_substring, path))
+    addr_index = {a: i for i, (a, _) in enumerate(lines)}
+    best = None
+    for i, (a, text) in enumerate(lines):
+        m = re.search(r"0x([0-9a-f]+)", text) if opcode(text) == "BRA" else None
+        if not m or int(m.group(1), 16) >= a or int(m.group(1), 16) not in addr_index:
+            continue
+        body = lines[addr_index[int(m.group(1), 16)]:i + 1]
+        # innermost, except that short spin loops (mbarrier / cp.async waits) may sit inside
+        nested = False
+        for a2, t2 in body[:-1]:
+            m2 = re.search(r"0x([0-9a-f]+)", t2) if opcode(t2) == "BRA" else None
+            if m2 and int(m2.group(1), 16) <= a2 and a2 - int(m2.group(1), 16) > 8 * 16:
+                nested = True
+        if nested:
+            continue
+        n_hot = sum(opcode(t) in hot for _, t in body)
+        if best is None or n_hot > best[0]:
+            best = (n_hot, body)
+    mix = {}
+    for _, t in best[1]:
+        mix[opcode(t)] = mix.get(opcode(t), 0) + 1
+    return mix
+
+
 def main():
     path = sys.argv[1]
+    if len(sys.argv) >= 4 and sys.argv[2] == "--kernel":   # any kernel: just the mix of its hottest loop
+        mix = loop_mix(path, sys.argv[3])
+        print("%s  %s  hottest innermost loop: %d instructions" % (path, sys.argv[3], sum(mix.values())))
+        print("  mix: " + ", ".join("%s %d" % kv for kv in sorted(mix.items(), key=lambda kv: -kv[1])))
+        return
     d, nc, p = (int(x) for x in sys.argv[2:5]) if len(sys.argv) >= 5 else (3, 1, 3)
     r = analyze(path, d, nc, p)
     print("%s  <D=%d NC=%d P=%d>  loop body: %d instructions" % (path, d, nc, p, r["body_len"]))
