@@ -9,10 +9,11 @@
 //     t   : D DFMA                      (init with -th)
 //     r   : 3 DADD   n = rint(t) by the 1.5*2^52 trick, r = t - n exact, |r| <= 1/2
 //     s   : 1 DMUL   s = r*r
-//     u   : 6 DFMA   u = sqrt2*cos(pi/2 r), minimax deg-6 in s      (cospi_poly.cuh)
+//     u   : 1 DADD + 4 DFMA   u ~ sqrt2*cos(pi/2 r): monic minimax polynomial of degree 5 in s
+//                             (cospi_poly.cuh; GSF_POLY_DEGREE=6 adds one DFMA, see below)
 //     y   : 1 DFMA   cos(pi r) = u*u - 1
 //     acc : NC DFMA  acc_a += A_a * (+-y), sign = parity of n (one integer IMAD on y's high word)
-// = D + 11 + NC FP64-pipe instructions per point*mode (15 for the 3-D scalar field).
+// = D + 10 + NC FP64-pipe instructions per point*mode (14 for the 3-D scalar field).
 //
 // Mapping.  One CTA = kThreads threads = a tile of P*kThreads/L points.  A group of L lanes shares
 // one point set and splits the modes (lane sub handles modes sub, sub+L, ...); partial sums are
@@ -48,27 +49,56 @@ constexpr double kMagic = 6755399441055744.0;  // 1.5 * 2^52
 enum Kind : int { kScalar = 0, kIncompr = 1, kFourier = 2 };
 
 // Polynomial form of the hot loop (cospi_poly.cuh):
-//   0: u = U(s) by 6 DFMA, y = u*u - 1.  The first Horner step fma(U6, s, U5) has TWO constant
-//      operands; a DFMA takes at most one from the constant bank / a uniform register, so ptxas
-//      keeps both in registers: three register-file reads = 3 issue cycles instead of 2.
-//   1: U = c*Q with Q monic: v = s + Q5 (DADD), 5 DFMA, w = v*v - 1/c^2; the factor c^2 is folded
-//      into the mode amplitudes by gsf_prep_modes.  Same FP64 instruction count, no instruction
-//      with three register sources in the polynomial.
+//   GSF_POLY_MONIC 0: u = U(s) by 6 DFMA, y = u*u - 1.  The first Horner step fma(U6, s, U5) has TWO
+//      constant operands; a DFMA takes at most one from the constant bank / a uniform register, so
+//      ptxas keeps both in registers: three register-file reads = 3 issue cycles instead of 2.
+//   GSF_POLY_MONIC 1 (default): U = c*Q with Q monic: v = s + Q_{deg-1} (DADD), deg-1 DFMA,
+//      w = v*v - 1/c^2; the factor c^2 is folded into the mode amplitudes by gsf_prep_modes.  No
+//      instruction with three register sources in the polynomial.
+//   GSF_POLY_DEGREE (monic form only): degree of U in s.
+//      6: |cos error| <= 6.5e-16 (3 ulp at 1) -- far below the rounding of the phase itself
+//         (|phi| * 1.1e-16) and 6 orders inside the 1e-9 sigma contract;
+//      5 (default): <= 2.2e-13 absolute per term, measured <= 1e-12 sigma against the oracle on
+//         every BASELINE config (tests/test_parity_gpu.py, profiles/poly_degree_r2.md) -- still three
+//         orders inside the contract, one DFMA (2 issue cycles of ~31) cheaper per point*mode;
+//      4: <= 1.9e-10 per term: too close to the contract, kept for the measurement only.
 #ifndef GSF_POLY_MONIC
 #define GSF_POLY_MONIC 1
 #endif
+#ifndef GSF_POLY_DEGREE
+#define GSF_POLY_DEGREE 5
+#endif
 constexpr bool kPolyMonic = GSF_POLY_MONIC != 0;
+// Every point x mode kernel is templated on the degree DEG.  Two are instantiated: kHiDeg for
+// small (launch-latency-bound) problems, where the extra DFMA is free, and kFastDeg for the
+// throughput-bound ones; the host picks ONE degree per call from the total work (choose_degree in
+// gsfield.cu), so chunking and device sharding never change a result.
+constexpr int kHiDeg = 6;
+constexpr int kFastDeg = kPolyMonic ? GSF_POLY_DEGREE : 6;
+static_assert(kFastDeg >= 4 && kFastDeg <= 6, "GSF_POLY_DEGREE must be 4, 5 or 6");
+// FP64-pipe instructions of one cos(pi t): 3 DADD (reduction) + DMUL + (DADD + (deg-1) DFMA | 6 DFMA) + DFMA
+__host__ __device__ constexpr int cos_slots(int deg) { return 3 + 1 + deg + 1; }
 // amplitude factor the pre-pass folds into the records of the point x mode kernels
-constexpr double kAmpFactor = kPolyMonic ? GSF_QS : 1.0;
-// the 7 constants handed to the kernels as SumArgs::coef (c0..c5: Horner constants, c6: see cospi_signed)
-__host__ __device__ inline void poly_constants(double *c)
+inline double amp_factor(int deg)
 {
-    if (kPolyMonic) {
-        c[0] = GSF_Q0; c[1] = GSF_Q1; c[2] = GSF_Q2; c[3] = GSF_Q3; c[4] = GSF_Q4; c[5] = GSF_Q5; c[6] = -(GSF_QE);
-    } else {
+    if (!kPolyMonic) return 1.0;
+    return deg == 4 ? GSF_Q4_S : deg == 5 ? GSF_Q5_S : GSF_Q6_S;
+}
+// the constants handed to the kernels as SumArgs::coef (c[0..deg-1]: Horner constants, c[6]: -1/c^2
+// for the monic form, U6 otherwise)
+inline void poly_constants(int deg, double *c)
+{
+    for (int i = 0; i < 8; ++i) c[i] = 0.0;
+    if (!kPolyMonic) {
         c[0] = GSF_U0; c[1] = GSF_U1; c[2] = GSF_U2; c[3] = GSF_U3; c[4] = GSF_U4; c[5] = GSF_U5; c[6] = GSF_U6;
+    } else if (deg == 4) {
+        c[0] = GSF_Q4_0; c[1] = GSF_Q4_1; c[2] = GSF_Q4_2; c[3] = GSF_Q4_3; c[6] = -(GSF_Q4_E);
+    } else if (deg == 5) {
+        c[0] = GSF_Q5_0; c[1] = GSF_Q5_1; c[2] = GSF_Q5_2; c[3] = GSF_Q5_3; c[4] = GSF_Q5_4; c[6] = -(GSF_Q5_E);
+    } else {
+        c[0] = GSF_Q6_0; c[1] = GSF_Q6_1; c[2] = GSF_Q6_2; c[3] = GSF_Q6_3; c[4] = GSF_Q6_4; c[5] = GSF_Q6_5;
+        c[6] = -(GSF_Q6_E);
     }
-    c[7] = 0.0;
 }
 
 // doubles per pre-processed mode record: kh[D], th, A[NC], padded to an even count so every
@@ -185,24 +215,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 // literals ptxas re-materialises them with UMOV pairs inside the mode loop, and every non-FP64
 // instruction there costs an issue cycle the FP64 pipe could have used.
 struct PolyCoef {
-    double c0, c1, c2, c3, c4, c5, c6;
+    double c[7];
 };
 // (-1)^rint(t) * cos(pi*r): cos(pi*t) for the reduced argument with the sign applied.
-// 11 FP64-pipe instructions + 1 integer multiply-add: adding parity<<31 to the high word
+// cos_slots(DEG) FP64-pipe instructions + 1 integer multiply-add: adding parity<<31 to the high word
 // modulo 2^32 is exactly an XOR of the sign bit.
+template <int DEG>
 __device__ __forceinline__ double cospi_signed(double t, const PolyCoef &c)
 {
     const double tn = __dadd_rn(t, kMagic);     // low mantissa bits = rint(t)
     const double nf = __dadd_rn(tn, -kMagic);   // rint(t) as a double
     const double r = __dadd_rn(t, -nf);         // exact, |r| <= 1/2
     const double s = __dmul_rn(r, r);
-    double u = kPolyMonic ? __dadd_rn(s, c.c5) : fma(c.c6, s, c.c5);
-    u = fma(u, s, c.c4);
-    u = fma(u, s, c.c3);
-    u = fma(u, s, c.c2);
-    u = fma(u, s, c.c1);
-    u = fma(u, s, c.c0);
-    const double y = kPolyMonic ? fma(u, u, c.c6) : fma(u, u, -1.0);   // monic: c6 = -1/c^2
+    double u = kPolyMonic ? __dadd_rn(s, c.c[DEG - 1]) : fma(c.c[6], s, c.c[5]);
+#pragma unroll
+    for (int q = DEG - 2; q >= 0; --q) u = fma(u, s, c.c[q]);
+    const double y = kPolyMonic ? fma(u, u, c.c[6]) : fma(u, u, -1.0);   // monic: c[6] = -1/c^2
     const uint32_t hi = static_cast<uint32_t>(__double2hiint(y)) +
                         (static_cast<uint32_t>(__double2loint(tn)) << 31);
     return __hiloint2double(static_cast<int>(hi), __double2loint(y));
@@ -242,7 +270,7 @@ __host__ __device__ constexpr int gsf_unroll() { return GSF_TUNE_UNROLL; }
 #endif
 
 // Body for one CTA tile starting at point tile0 (P points per thread).
-template <int D, int NC, int P, int L>
+template <int D, int NC, int P, int L, int DEG>
 __device__ __forceinline__ void sum_tile(const SumArgs &a, const int64_t tile0,
                                          double (*s_rec)[kModeBlock * rec_doubles(D, NC)], uint64_t *s_bar)
 {
@@ -271,7 +299,7 @@ __device__ __forceinline__ void sum_tile(const SumArgs &a, const int64_t tile0,
 #pragma unroll
         for (int c = 0; c < NC; ++c) acc[p][c] = sub == 0 ? a.offset[c < 3 ? c : 0] : 0.0;
 
-    const PolyCoef coef = {a.coef[0], a.coef[1], a.coef[2], a.coef[3], a.coef[4], a.coef[5], a.coef[6]};
+    const PolyCoef coef = {{a.coef[0], a.coef[1], a.coef[2], a.coef[3], a.coef[4], a.coef[5], a.coef[6]}};
 
     // ---- mode ring: thread 0 is the producer
     const int64_t n_blocks = (a.n_modes + kModeBlock - 1) / kModeBlock;
@@ -318,7 +346,7 @@ __device__ __forceinline__ void sum_tile(const SumArgs &a, const int64_t tile0,
                     double t = nth;
 #pragma unroll
                     for (int d = 0; d < D; ++d) t = fma(kh[d], x[p][d], t);
-                    const double y = cospi_signed(t, coef);
+                    const double y = cospi_signed<DEG>(t, coef);
 #pragma unroll
                     for (int c = 0; c < NC; ++c) acc[p][c] = fma(amp[c], y, acc[p][c]);
                 }
@@ -343,20 +371,15 @@ __device__ __forceinline__ void sum_tile(const SumArgs &a, const int64_t tile0,
                 sq[p] = __dmul_rn(r, r);
             }
 #pragma unroll
-            for (int p = 0; p < P; ++p) u[p] = kPolyMonic ? __dadd_rn(sq[p], coef.c5) : fma(coef.c6, sq[p], coef.c5);
+            for (int p = 0; p < P; ++p)
+                u[p] = kPolyMonic ? __dadd_rn(sq[p], coef.c[DEG - 1]) : fma(coef.c[6], sq[p], coef.c[5]);
 #pragma unroll
-            for (int p = 0; p < P; ++p) u[p] = fma(u[p], sq[p], coef.c4);
+            for (int q = DEG - 2; q >= 0; --q)
 #pragma unroll
-            for (int p = 0; p < P; ++p) u[p] = fma(u[p], sq[p], coef.c3);
-#pragma unroll
-            for (int p = 0; p < P; ++p) u[p] = fma(u[p], sq[p], coef.c2);
-#pragma unroll
-            for (int p = 0; p < P; ++p) u[p] = fma(u[p], sq[p], coef.c1);
-#pragma unroll
-            for (int p = 0; p < P; ++p) u[p] = fma(u[p], sq[p], coef.c0);
+                for (int p = 0; p < P; ++p) u[p] = fma(u[p], sq[p], coef.c[q]);
 #pragma unroll
             for (int p = 0; p < P; ++p) {
-                const double y = kPolyMonic ? fma(u[p], u[p], coef.c6)           // cos(pi r) / c^2
+                const double y = kPolyMonic ? fma(u[p], u[p], coef.c[6])         // cos(pi r) / c^2
                                             : fma(u[p], u[p], -1.0);             // cos(pi r)
                 const uint32_t hi = static_cast<uint32_t>(__double2hiint(y)) +
                                     (static_cast<uint32_t>(__double2loint(tn[p])) << 31);
@@ -393,7 +416,7 @@ __device__ __forceinline__ void sum_tile(const SumArgs &a, const int64_t tile0,
 // thread (a third of the work for P = 3).  The block scheduler hands out CTAs in index order, so
 // the short tiles run last: the machine drains in steps of the short tile, which removes most of
 // the end-of-kernel imbalance (17 vs 18 long CTAs per SM at C2) and partial-occupancy tail.
-template <int D, int NC, int P, int L>
+template <int D, int NC, int P, int L, int DEG>
 __global__ void __launch_bounds__(kThreads) gsf_sum_kernel(SumArgs a)
 {
     constexpr int R = rec_doubles(D, NC);
@@ -402,13 +425,13 @@ __global__ void __launch_bounds__(kThreads) gsf_sum_kernel(SumArgs a)
     constexpr int kTile = (kThreads / L) * P;        // points per long tile
     const int64_t b = blockIdx.x;
 #ifdef GSF_NO_HYBRID_TAIL
-    sum_tile<D, NC, P, L>(a, b * kTile, s_rec, s_bar);
+    sum_tile<D, NC, P, L, DEG>(a, b * kTile, s_rec, s_bar);
 #else
     if (P <= kTailP || L > 1 || b < a.n_big) {
-        sum_tile<D, NC, P, L>(a, b * kTile, s_rec, s_bar);
+        sum_tile<D, NC, P, L, DEG>(a, b * kTile, s_rec, s_bar);
     } else {
-        sum_tile<D, NC, kTailP, (P <= kTailP ? L : 1)>(a, a.n_big * kTile + (b - a.n_big) * (kThreads * kTailP), s_rec,
-                                                       s_bar);
+        sum_tile<D, NC, kTailP, (P <= kTailP ? L : 1), DEG>(a, a.n_big * kTile + (b - a.n_big) * (kThreads * kTailP),
+                                                            s_rec, s_bar);
     }
 #endif
 }
@@ -418,20 +441,21 @@ __global__ void __launch_bounds__(kThreads) gsf_sum_kernel(SumArgs a)
 // run-time loop, mode records and the point's coordinates come through L1 (`__ldg`; a warp reads one
 // record as a broadcast and 32 consecutive points per coordinate row).  Same recipe, same record
 // layout and the same mode order as gsf_sum_kernel<D,1,1,1>.
+template <int DEG>
 __global__ void __launch_bounds__(kThreads) gsf_sum_kernel_anyd(SumArgs a)
 {
     const int64_t j = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (j >= a.n_points) return;
     const int D = a.dim;
     const int R = rec_doubles(D, 1);
-    const PolyCoef coef = {a.coef[0], a.coef[1], a.coef[2], a.coef[3], a.coef[4], a.coef[5], a.coef[6]};
+    const PolyCoef coef = {{a.coef[0], a.coef[1], a.coef[2], a.coef[3], a.coef[4], a.coef[5], a.coef[6]}};
     const double *x = a.pos + j * a.ps1;
     double acc = a.offset[0];
     for (int64_t i = 0; i < a.n_modes; ++i) {
         const double *m = a.rec + i * R;
         double t = __ldg(m + D);
         for (int d = 0; d < D; ++d) t = fma(__ldg(m + d), __ldg(x + d * a.ps0), t);
-        acc = fma(__ldg(m + D + 1), cospi_signed(t, coef), acc);
+        acc = fma(__ldg(m + D + 1), cospi_signed<DEG>(t, coef), acc);
     }
     a.out[j * a.os1] = acc;
 }

@@ -11,6 +11,7 @@
 // steps, device-resident memory skips the copies.  With several devices configured the points are
 // sharded contiguously, one host thread per device, no collective.
 #include <cuda_runtime.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <chrono>
@@ -20,6 +21,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <deque>
+#include <memory>
 #include <condition_variable>
 #include <functional>
 #include <map>
@@ -66,45 +69,58 @@ int fail(int code, const char *fmt, ...)
 // kernel table
 typedef void (*SumKernel)(SumArgs);
 
-template <int D, int NC>
+// Every (P, L) variant exists at the high degree; the throughput degree (gsf::kFastDeg) only for
+// L = 1 -- it is chosen for large problems only, and those never split the modes over lanes.
+template <int D, int NC, int DEG>
 SumKernel pick_pl(int P, int L)
 {
 #define GSF_V(p, l) \
-    if (P == p && L == l) return gsf::gsf_sum_kernel<D, NC, p, l>;
+    if (P == p && L == l) return gsf::gsf_sum_kernel<D, NC, p, l, DEG>;
     GSF_V(4, 1) GSF_V(3, 1) GSF_V(2, 1) GSF_V(1, 1)
-    GSF_V(2, 2) GSF_V(2, 4) GSF_V(2, 8) GSF_V(2, 16) GSF_V(2, 32)
-    GSF_V(1, 2) GSF_V(1, 4) GSF_V(1, 8) GSF_V(1, 16) GSF_V(1, 32)
+    if constexpr (DEG == gsf::kHiDeg) {
+        GSF_V(2, 2) GSF_V(2, 4) GSF_V(2, 8) GSF_V(2, 16) GSF_V(2, 32)
+        GSF_V(1, 2) GSF_V(1, 4) GSF_V(1, 8) GSF_V(1, 16) GSF_V(1, 32)
+    }
 #undef GSF_V
     return nullptr;
 }
 
-template <int D>
+template <int D, int DEG>
 SumKernel pick_hi(int P, int L)   // dim 4..8: fewer variants
 {
-    if (P == 1 && L == 1) return gsf::gsf_sum_kernel<D, 1, 1, 1>;
-    if (P == 1 && L == 4) return gsf::gsf_sum_kernel<D, 1, 1, 4>;
-    if (P == 1 && L == 32) return gsf::gsf_sum_kernel<D, 1, 1, 32>;
+    if (P == 1 && L == 1) return gsf::gsf_sum_kernel<D, 1, 1, 1, DEG>;
+    if constexpr (DEG == gsf::kHiDeg) {
+        if (P == 1 && L == 4) return gsf::gsf_sum_kernel<D, 1, 1, 4, DEG>;
+        if (P == 1 && L == 32) return gsf::gsf_sum_kernel<D, 1, 1, 32, DEG>;
+    }
     return nullptr;
 }
 
-SumKernel pick_kernel(int dim, bool incompr, int P, int L)
+template <int DEG>
+SumKernel pick_kernel_deg(int dim, bool incompr, int P, int L)
 {
     if (incompr) {
-        if (dim == 2) return pick_pl<2, 2>(P, L);
-        if (dim == 3) return pick_pl<3, 3>(P, L);
+        if (dim == 2) return pick_pl<2, 2, DEG>(P, L);
+        if (dim == 3) return pick_pl<3, 3, DEG>(P, L);
         return nullptr;
     }
     switch (dim) {
-        case 1: return pick_pl<1, 1>(P, L);
-        case 2: return pick_pl<2, 1>(P, L);
-        case 3: return pick_pl<3, 1>(P, L);
-        case 4: return pick_hi<4>(P, L);
-        case 5: return pick_hi<5>(P, L);
-        case 6: return pick_hi<6>(P, L);
-        case 7: return pick_hi<7>(P, L);
-        case 8: return pick_hi<8>(P, L);
+        case 1: return pick_pl<1, 1, DEG>(P, L);
+        case 2: return pick_pl<2, 1, DEG>(P, L);
+        case 3: return pick_pl<3, 1, DEG>(P, L);
+        case 4: return pick_hi<4, DEG>(P, L);
+        case 5: return pick_hi<5, DEG>(P, L);
+        case 6: return pick_hi<6, DEG>(P, L);
+        case 7: return pick_hi<7, DEG>(P, L);
+        case 8: return pick_hi<8, DEG>(P, L);
     }
     return nullptr;
+}
+
+SumKernel pick_kernel(int dim, bool incompr, int P, int L, int deg = gsf::kHiDeg)
+{
+    if (deg == gsf::kFastDeg && gsf::kFastDeg != gsf::kHiDeg) return pick_kernel_deg<gsf::kFastDeg>(dim, incompr, P, L);
+    return pick_kernel_deg<gsf::kHiDeg>(dim, incompr, P, L);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -140,6 +156,10 @@ struct DeviceCtx {
     bool rec_valid = false;
     double *g_axes = nullptr, *g_E0 = nullptr, *g_E1 = nullptr, *g_F = nullptr;   // grid-path tables
     size_t g_axes_cap = 0, g_E0_cap = 0, g_E1_cap = 0, g_F_cap = 0;
+    double *ring_in = nullptr, *ring_out = nullptr;   // pinned staging rings of the chunk pipeline
+    size_t ring_in_cap = 0, ring_out_cap = 0;
+    std::vector<cudaEvent_t> ev_ring_in, ev_ring_out;   // per ring slot: H2D consumed it / D2H filled it
+    int staging_threads = 0;             // host threads that staged pageable memory in the last call
     double *g_counter0 = nullptr;        // scratch of the device-side grid detection
     size_t g_counter0_cap = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof;   // pool of timing events
@@ -160,6 +180,7 @@ struct Context {
     std::vector<DeviceCtx *> dctx;       // indexed by device id
     int64_t chunk_points = 0;
     int force_p = 0, force_l = 0;
+    int poly_degree = 0;                 // 0: choose_degree's rule; else forced (gsf_set_poly_degree / GSF_POLY_DEGREE)
     bool profiling = false;
     int grid_detect = -1;                // -1: env GSF_GRID_DETECT (default on), 0 off, 1 on
     gsf_stats last{};
@@ -216,9 +237,14 @@ int get_device_ctx(int dev, DeviceCtx **out)
         cudaDeviceProp prop;
         GSF_CUDA(cudaGetDeviceProperties(&prop, dev));
         d->sm_count = prop.multiProcessorCount;
-        if (prop.major < 10)
-            return fail(GSF_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only",
+        // the library carries sm_100a SASS only (no PTX): any other architecture -- older or newer --
+        // would fail at the first launch with "no kernel image"; say so here instead
+        cudaFuncAttributes fa;
+        if (prop.major != 10 || cudaFuncGetAttributes(&fa, gsf::gsf_prep_modes) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(GSF_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a (B200) only",
                         dev, prop.major, prop.minor);
+        }
         for (int s = 0; s < kSlots; ++s) {
             GSF_CUDA(cudaStreamCreateWithFlags(&d->slot[s].stream, cudaStreamNonBlocking));
             GSF_CUDA(cudaEventCreateWithFlags(&d->slot[s].ev_h2d, cudaEventDisableTiming));
@@ -259,6 +285,10 @@ void free_device_ctx(DeviceCtx *d)
         if (d->g_E1) cudaFree(d->g_E1);
         if (d->g_F) cudaFree(d->g_F);
         if (d->g_counter0) cudaFree(d->g_counter0);
+        if (d->ring_in) cudaFreeHost(d->ring_in);
+        if (d->ring_out) cudaFreeHost(d->ring_out);
+        for (cudaEvent_t e : d->ev_ring_in) cudaEventDestroy(e);
+        for (cudaEvent_t e : d->ev_ring_out) cudaEventDestroy(e);
         for (auto &pr : d->prof) {
             cudaEventDestroy(pr.first);
             cudaEventDestroy(pr.second);
@@ -269,6 +299,21 @@ void free_device_ctx(DeviceCtx *d)
         cudaEventDestroy(d->prep_end);
     }
     delete d;
+}
+
+int ensure_ring_events(DeviceCtx &d, int depth)
+{
+    while ((int)d.ev_ring_in.size() < depth) {
+        cudaEvent_t e;
+        GSF_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        d.ev_ring_in.push_back(e);
+    }
+    while ((int)d.ev_ring_out.size() < depth) {
+        cudaEvent_t e;
+        GSF_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        d.ev_ring_out.push_back(e);
+    }
+    return GSF_OK;
 }
 
 // memory kind of a user pointer: 0 pageable host, 1 pinned host, 2 device/managed
@@ -305,6 +350,7 @@ struct Problem {
     int threads_hint = 0;
     int peer_owner = -1;                 // >= 0: device arrays live on this device, peers may read them
     bool zero_copy = false;              // pos/out are mapped pinned host memory read over PCIe
+    int deg = gsf::kHiDeg;               // degree of the cosine polynomial, ONE per call (choose_degree)
     double scale = 1.0;                  // out = scale * sum + offset[a]   
     double offset[3] = {0.0, 0.0, 0.0};
     int nc() const { return kind == gsf::kIncompr ? dim : 1; }
@@ -341,7 +387,7 @@ void choose_variant(const DeviceCtx &d, const Problem &p, int64_t m_launch, bool
 {
     Context &c = ctx();
     const bool inc = p.kind == gsf::kIncompr;
-    if (c.force_p > 0 && c.force_l > 0 && pick_kernel(p.dim, inc, c.force_p, c.force_l)) {
+    if (c.force_p > 0 && c.force_l > 0 && pick_kernel(p.dim, inc, c.force_p, c.force_l, p.deg)) {
         *P = c.force_p;
         *L = c.force_l;
         return;
@@ -373,8 +419,26 @@ void choose_variant(const DeviceCtx &d, const Problem &p, int64_t m_launch, bool
         //  and L = 1 keeps every point's summation order independent of chunking / device count)
         while (bestL < 32 && ctas1 * bestL < 2 * d.sm_count && p.N >= 32 * bestL) bestL *= 2;
     }
+    if (p.deg != gsf::kHiDeg) bestL = 1;   // the throughput degree ships L = 1 variants only
     *P = bestP;
     *L = bestL;
+}
+
+// Degree of the cosine polynomial for one call (gsf_kernels.cuh): the throughput degree when the
+// FP64 pipe is what the caller waits for, the high degree for small problems where launch latency
+// dominates and the extra DFMA is free.  Decided ONCE per call from the whole problem -- never per
+// chunk or per device shard -- so that results do not depend on chunking or on the device count.
+int choose_degree(const Problem &p)
+{
+    Context &c = ctx();
+    static const int env_deg = []() { const char *e = getenv("GSF_POLY_DEGREE"); return e && *e ? atoi(e) : 0; }();
+    const int forced = c.poly_degree ? c.poly_degree : env_deg;
+    const bool lanes_forced = c.force_p > 0 && c.force_l > 1;
+    if (forced == gsf::kHiDeg || forced == gsf::kFastDeg)
+        return lanes_forced || p.dim > gsf::kMaxTemplateDim ? gsf::kHiDeg : forced;
+    if (lanes_forced || p.dim > gsf::kMaxTemplateDim) return gsf::kHiDeg;
+    const double pm = (double)p.N * (double)p.M;
+    return pm >= 134217728.0 && p.M >= 65536 ? gsf::kFastDeg : gsf::kHiDeg;   // 2^27 point*modes ~ 0.1 ms of kernel
 }
 
 int launch_sum(DeviceCtx &d, const Problem &p, const double *kpos, int64_t ps0, int64_t ps1, double *kout,
@@ -382,8 +446,8 @@ int launch_sum(DeviceCtx &d, const Problem &p, const double *kpos, int64_t ps0, 
 {
     const bool anyd = p.dim > gsf::kMaxTemplateDim;
     if (anyd) { P = 1; L = 1; }
-    SumKernel fn = anyd ? gsf::gsf_sum_kernel_anyd : pick_kernel(p.dim, p.kind == gsf::kIncompr, P, L);
-    if (!fn) return fail(GSF_ERR_ARG, "no kernel variant dim=%d P=%d L=%d", p.dim, P, L);
+    SumKernel fn = anyd ? gsf::gsf_sum_kernel_anyd<gsf::kHiDeg> : pick_kernel(p.dim, p.kind == gsf::kIncompr, P, L, p.deg);
+    if (!fn) return fail(GSF_ERR_ARG, "no kernel variant dim=%d P=%d L=%d degree=%d", p.dim, P, L, p.deg);
     SumArgs a;
     a.dim = p.dim;
     a.rec = d.d_rec;
@@ -392,7 +456,7 @@ int launch_sum(DeviceCtx &d, const Problem &p, const double *kpos, int64_t ps0, 
     a.n_points = m;
     a.out = kout; a.os0 = os0; a.os1 = os1;
     for (int c = 0; c < 3; ++c) a.offset[c] = p.offset[c];
-    gsf::poly_constants(a.coef);
+    gsf::poly_constants(anyd ? gsf::kHiDeg : p.deg, a.coef);
     // long tiles (P points per thread) first, then short tiles (1 point per thread) for the last
     // `tail` resident waves so that the machine drains in small steps (see gsf_sum_kernel)
     const int64_t tile = (int64_t)P * (kThreads / L);
@@ -435,8 +499,8 @@ int launch_sum(DeviceCtx &d, const Problem &p, const double *kpos, int64_t ps0, 
 // Upload (if host) and pre-process the modes on `st`.  Host arrays are gathered into a contiguous
 // temporary and copied with a pageable cudaMemcpyAsync (staged by the driver before it returns).
 // `amp_factor`: what the consumer of the records wants folded into the amplitudes besides p.scale
-// (gsf::kAmpFactor for the point x mode kernels, 1 for the structured-grid tables).
-int prepare_modes(DeviceCtx &d, const Problem &p, cudaStream_t st, double amp_factor = gsf::kAmpFactor)
+// (gsf::amp_factor(p.deg) for the point x mode kernels, 1 for the structured-grid tables).
+int prepare_modes(DeviceCtx &d, const Problem &p, cudaStream_t st, double amp_factor)
 {
     const int64_t N = p.N;
     const double scale = amp_factor == 1.0 ? p.scale : p.scale * amp_factor;
@@ -509,6 +573,7 @@ void reset_call_counters(DeviceCtx &d)
 {
     d.h2d_bytes = d.d2h_bytes = 0;
     d.launches = d.chunks = 0;
+    d.staging_threads = 0;
     d.prof_used = 0;
     d.prep_timed = false;
     d.status = GSF_OK;
@@ -535,166 +600,7 @@ struct DrainOnError {
     }
 };
 
-// ---------------------------------------------------------------------------------------------
-// Persistent host worker pool for the pageable-memory staging copies (gather into / scatter out
-// of the pinned ring).  One memcpy thread moves ~10 GB/s, a PCIe 5 x16 link ~55 GB/s, so staging
-// is what bounds the pageable path; `num_threads` of the reference signature caps the workers.
-class HostPool {
-  public:
-    ~HostPool()
-    {
-        {
-            std::lock_guard<std::mutex> l(mu_);
-            stop_ = true;
-        }
-        cv_work_.notify_all();
-        for (auto &t : workers_) t.join();
-    }
-    // run f(part) for part in [0, n_parts) on up to n_threads threads (the caller is one of them)
-    void run(int n_parts, int n_threads, const std::function<void(int)> &f)
-    {
-        if (n_parts <= 1 || n_threads <= 1) {
-            for (int i = 0; i < n_parts; ++i) f(i);
-            return;
-        }
-        std::lock_guard<std::mutex> serial(run_mu_);
-        {
-            std::lock_guard<std::mutex> l(mu_);
-            while ((int)workers_.size() < n_threads - 1) workers_.emplace_back([this]() { worker(); });
-            job_ = &f;
-            total_ = n_parts;
-            next_.store(0);
-            done_.store(0);
-            gen_.fetch_add(1, std::memory_order_release);
-        }
-        cv_work_.notify_all();
-        drain();
-        std::unique_lock<std::mutex> l(mu_);
-        cv_done_.wait(l, [this]() { return done_.load() >= total_; });
-        job_ = nullptr;
-    }
-
-  private:
-    void drain()
-    {
-        for (;;) {
-            const int i = next_.fetch_add(1);
-            if (i >= total_) break;
-            (*job_)(i);
-            if (done_.fetch_add(1) + 1 >= total_) {
-                std::lock_guard<std::mutex> l(mu_);
-                cv_done_.notify_all();
-            }
-        }
-    }
-    void worker()
-    {
-        uint64_t seen = 0;
-        for (;;) {
-            // stay hot for ~100 us after a job: calls arrive back to back, and a condition-variable
-            // wake-up costs tens of microseconds on a virtualised host
-            bool got = false;
-            const auto t_end = std::chrono::steady_clock::now() + std::chrono::microseconds(100);
-            while (std::chrono::steady_clock::now() < t_end) {
-                if (gen_.load(std::memory_order_acquire) != seen || stop_) { got = true; break; }
-#if defined(__x86_64__)
-                __builtin_ia32_pause();
-#endif
-            }
-            if (!got) {
-                std::unique_lock<std::mutex> l(mu_);
-                cv_work_.wait(l, [&]() { return stop_ || gen_.load() != seen; });
-            }
-            if (stop_) return;
-            seen = gen_.load(std::memory_order_acquire);
-            drain();
-        }
-    }
-    std::mutex mu_, run_mu_;
-    std::condition_variable cv_work_, cv_done_;
-    std::vector<std::thread> workers_;
-    const std::function<void(int)> *job_ = nullptr;
-    int total_ = 0;
-    std::atomic<int> next_{0}, done_{0};
-    std::atomic<uint64_t> gen_{0};
-    std::atomic<bool> stop_{false};
-};
-
-HostPool &host_pool()
-{
-    static HostPool *p = new HostPool();   // leaked on purpose: no join during static destruction
-    return *p;
-}
-
-int staging_threads(int hint, int n_devices)
-{
-    if (n_devices > 1) return 1;   // one staging thread per device already
-    int hw = (int)std::thread::hardware_concurrency();
-    // measured on the 16-vCPU B200 host (tools/pageable_probe.py): 2 threads beat 1, 4, 8 and 16 --
-    // condition-variable wake-ups of more workers cost more than the extra memcpy bandwidth buys
-    int t = hw >= 4 ? 2 : 1;
-    static const int env_t = []() { const char *e = getenv("GSF_STAGING_THREADS"); return e && *e ? atoi(e) : 0; }();
-    if (env_t > 0) t = env_t;
-    if (hint > 0) t = std::min(t, hint);
-    return t;
-}
-
-// split [0, cnt) into parts of >= 16k points for the pool
-inline int staging_parts(int64_t cnt, int threads) { return (int)std::max<int64_t>(1, std::min<int64_t>(threads, cnt / 16384)); }
-
-// gather rows [j0, j0+cnt) of a strided (dim, M) host array into `dst` (row stride cnt)
-void gather_pos(const Problem &p, int64_t j0, int64_t cnt, double *dst, int threads)
-{
-    const int parts = staging_parts(cnt, threads);
-    host_pool().run(parts, threads, [&](int part) {
-        const int64_t b = cnt * part / parts, e = cnt * (part + 1) / parts;
-        for (int a = 0; a < p.dim; ++a) {
-            const double *src = p.pos + a * p.ps0 + (j0 + b) * p.ps1;
-            double *row = dst + (size_t)a * cnt + b;
-            if (p.ps1 == 1) {
-                memcpy(row, src, (size_t)(e - b) * sizeof(double));
-            } else {
-                for (int64_t j = 0; j < e - b; ++j) row[j] = src[j * p.ps1];
-            }
-        }
-    });
-}
-
-struct OutLayout {
-    bool aos;           // device chunk is cnt records of nc doubles (else nc rows of cnt)
-    bool direct;        // D2H straight into the user's buffer
-};
-
-// scatter a finished staging-out chunk into the user's (strided) output
-void scatter_out(const Problem &p, const OutLayout &lay, int64_t j0, int64_t cnt, const double *src, int threads)
-{
-    const int nc = p.nc();
-    const int parts = staging_parts(cnt, threads);
-    host_pool().run(parts, threads, [&](int part) {
-        const int64_t b = cnt * part / parts, e = cnt * (part + 1) / parts, n = e - b;
-        if (nc == 1) {
-            if (p.os1 == 1) {
-                memcpy(p.out + j0 + b, src + b, (size_t)n * sizeof(double));
-            } else {
-                for (int64_t j = b; j < e; ++j) p.out[(j0 + j) * p.os1] = src[j];
-            }
-            return;
-        }
-        if (lay.aos) {   // os0 == 1, os1 == nc: contiguous records
-            memcpy(p.out + (j0 + b) * p.os1, src + (size_t)b * nc, (size_t)n * nc * sizeof(double));
-            return;
-        }
-        for (int a = 0; a < nc; ++a) {
-            const double *row = src + (size_t)a * cnt + b;
-            double *dst = p.out + a * p.os0 + (j0 + b) * p.os1;
-            if (p.os1 == 1) {
-                memcpy(dst, row, (size_t)n * sizeof(double));
-            } else {
-                for (int64_t j = 0; j < n; ++j) dst[j * p.os1] = row[j];
-            }
-        }
-    });
-}
+#include "gsf_host_staging.inc"
 
 // Chunk sizes for streaming m points through the pipeline slots (see run_shard).
 std::vector<int64_t> chunk_schedule(int64_t m, bool single_launch, int64_t forced_chunk)
@@ -728,6 +634,13 @@ std::vector<int64_t> chunk_schedule(int64_t m, bool single_launch, int64_t force
 }
 
 // Process points [j_beg, j_end) of the problem on device d (host- or device-resident pos/out).
+//
+// Host-resident points stream through the device in chunks.  Chunk c runs on stream c % 3 with that
+// stream's device buffers:  H2D -> kernel -> D2H, so the copies of neighbouring chunks overlap the
+// kernel on the two copy engines.  Pageable memory goes through pinned rings (`ring_in` / `ring_out`
+// slots, deeper than the stream count so that staging can run ahead of the GPU) filled and drained
+// by the Stager crew (gsf_host_staging.inc); this thread only waits for "chunk c staged", issues,
+// and publishes event completions.  Pinned user memory skips the rings, device memory the copies.
 int run_shard(DeviceCtx &d, const Problem &p, int64_t j_beg, int64_t j_end, int pos_kind, int out_kind,
               int *P_used, int *L_used, int host_threads)
 {
@@ -740,20 +653,28 @@ int run_shard(DeviceCtx &d, const Problem &p, int64_t j_beg, int64_t j_end, int 
 
     cudaStream_t s0 = d.slot[0].stream;
     if (d.ws_used) GSF_CUDA(cudaStreamWaitEvent(s0, d.ev_ws, 0));
-    if ((rc = prepare_modes(d, p, s0))) return rc;
-    GSF_CUDA(cudaEventRecord(d.ev_modes, s0));
-    for (int s = 1; s < kSlots; ++s) GSF_CUDA(cudaStreamWaitEvent(d.slot[s].stream, d.ev_modes, 0));
+    if ((rc = prepare_modes(d, p, s0, gsf::amp_factor(p.deg)))) return rc;
 
     const bool pos_dev = pos_kind == 2, out_dev = out_kind == 2;
-    // Chunk schedule.  Device-resident both ways => one launch.  Otherwise the points stream through
-    // the three pipeline slots: the first chunks are small and double in size (the first kernel
-    // starts after a ~0.8 MB copy instead of waiting for megabytes), the middle runs at `cap`
-    // points per chunk (long kernels, P = 3 tiles), and the last chunks halve again so that little
-    // D2H is left exposed after the final kernel.  gsf_set_chunk_points(n) forces a fixed size.
+    // Chunk schedule.  Device-resident both ways => one launch.  Otherwise the first chunks are small
+    // and double in size (the first kernel starts after a ~0.8 MB copy instead of waiting for
+    // megabytes), the middle runs at `cap` points per chunk (long kernels, P = 3 tiles), and the last
+    // chunks halve again so that little D2H is left exposed after the final kernel.
+    // gsf_set_chunk_points(n) forces a fixed size.
     std::vector<int64_t> sizes = chunk_schedule(m_shard, pos_dev && out_dev, ctx().chunk_points);
     const int64_t n_chunks = (int64_t)sizes.size();
     int64_t chunk = 0;
-    for (int64_t c : sizes) chunk = std::max(chunk, c);
+    std::vector<int64_t> starts;
+    int64_t j_run = j_beg;
+    for (int64_t c : sizes) {
+        starts.push_back(j_run);
+        j_run += c;
+        chunk = std::max(chunk, c);
+    }
+    if (n_chunks > 1) {   // (a single launch runs on s0 itself)
+        GSF_CUDA(cudaEventRecord(d.ev_modes, s0));
+        for (int s = 1; s < kSlots; ++s) GSF_CUDA(cudaStreamWaitEvent(d.slot[s].stream, d.ev_modes, 0));
+    }
 
     // GSF_PAGEABLE_DIRECT=1: hand pageable memory straight to cudaMemcpyAsync (the driver stages it)
     static const bool pageable_direct = []() { const char *e = getenv("GSF_PAGEABLE_DIRECT"); return e && e[0] == '1'; }();
@@ -768,46 +689,85 @@ int run_shard(DeviceCtx &d, const Problem &p, int64_t j_beg, int64_t j_end, int 
     *P_used = P;
     *L_used = L;
 
-    struct Pending { int64_t j0, cnt; bool live; } pend[kSlots] = {};
-    bool slot_in_used[kSlots] = {false, false, false};
+    // ---- staging crew
+    const bool stage_in = !pos_dev && !direct_in, stage_out = !out_dev && !lay.direct;
+    std::shared_ptr<Stager> sg;
+    struct CrewGuard {   // on any exit: no worker may still be copying from / into the caller's arrays
+        std::shared_ptr<Stager> *s;
+        ~CrewGuard() { if (*s) (*s)->shut_down(); }
+    } crew_guard{&sg};
+    if (stage_in || stage_out) {
+        sg = std::make_shared<Stager>();
+        sg->p = p;
+        sg->lay = lay;
+        sg->stage_in = stage_in;
+        sg->stage_out = stage_out;
+        sg->plan(sizes, j_beg);
+        const int depth = (int)std::min<int64_t>(n_chunks, n_chunks <= kSlots ? kSlots : 5);
+        if (stage_in) {
+            sg->ring_in = depth;
+            sg->slot_in = (size_t)p.dim * chunk;
+            if ((rc = ensure_cap(&d.ring_in, &d.ring_in_cap, sg->slot_in * depth, true))) return rc;
+            sg->h_in = d.ring_in;
+        }
+        if (stage_out) {
+            sg->ring_out = depth;
+            sg->slot_out = (size_t)nc * chunk;
+            if ((rc = ensure_cap(&d.ring_out, &d.ring_out_cap, sg->slot_out * depth, true))) return rc;
+            sg->h_out = d.ring_out;
+        }
+        if ((rc = ensure_ring_events(d, depth))) return rc;
+        // workers beyond this thread: none for small jobs (a wake-up costs more than the copy)
+        const int64_t staged_bytes = ((stage_in ? p.dim : 0) + (stage_out ? nc : 0)) * m_shard * 8;
+        const int helpers = staged_bytes >= (1 << 20) ? std::min<int64_t>(host_threads - 1, sg->total_parts - 1) : 0;
+        d.staging_threads = 1 + std::max(0, helpers);
+        if (helpers > 0) host_pool().submit(sg, helpers);
+    }
+    int64_t in_polled = 0, out_polled = 0, issued = 0;
+    // publish event completions to the crew (never blocks)
+    auto poll = [&]() {
+        if (stage_in)
+            while (in_polled < issued && cudaEventQuery(d.ev_ring_in[(size_t)(in_polled % sg->ring_in)]) == cudaSuccess)
+                sg->in_released.store(++in_polled, std::memory_order_release);
+        if (stage_out)
+            while (out_polled < issued && cudaEventQuery(d.ev_ring_out[(size_t)(out_polled % sg->ring_out)]) == cudaSuccess)
+                sg->out_ready.store(++out_polled, std::memory_order_release);
+    };
+    // wait for a crew condition, helping with the work while waiting
+    auto wait_for = [&](const std::function<bool()> &ready, int64_t help_upto) {
+        int idle = 0;
+        while (!ready()) {
+            poll();
+            if (sg->step(help_upto)) { idle = 0; continue; }
+            if (++idle < 4000) cpu_relax(); else std::this_thread::yield();
+        }
+    };
 
-    int64_t j_next = j_beg;
     for (int64_t c = 0; c < n_chunks; ++c) {
         const int si = (int)(c % kSlots);
         Slot &sl = d.slot[si];
         cudaStream_t st = sl.stream;
-        const int64_t j0 = j_next;
         const int64_t cnt = sizes[(size_t)c];
-        j_next += cnt;
-
-        // drain the staging-out buffer of the chunk that used this slot last
-        if (pend[si].live) {
-            GSF_CUDA(cudaEventSynchronize(sl.ev_done));
-            scatter_out(p, lay, pend[si].j0, pend[si].cnt, sl.h_out, host_threads);
-            pend[si].live = false;
-        }
+        const int64_t jc = starts[(size_t)c];
 
         // ---- input
         const double *kpos;
         int64_t kps0, kps1;
         if (pos_dev) {
-            kpos = p.pos + j0 * p.ps1;
+            kpos = p.pos + jc * p.ps1;
             kps0 = p.ps0;
             kps1 = p.ps1;
         } else {
             if ((rc = ensure_cap(&sl.d_pos, &sl.d_pos_cap, (size_t)p.dim * cnt, false))) return rc;
             if (direct_in) {
                 for (int a = 0; a < p.dim; ++a)
-                    GSF_CUDA(cudaMemcpyAsync(sl.d_pos + (size_t)a * cnt, p.pos + a * p.ps0 + j0,
+                    GSF_CUDA(cudaMemcpyAsync(sl.d_pos + (size_t)a * cnt, p.pos + a * p.ps0 + jc,
                                              (size_t)cnt * sizeof(double), cudaMemcpyHostToDevice, st));
             } else {
-                if ((rc = ensure_cap(&sl.h_pos, &sl.h_pos_cap, (size_t)p.dim * cnt, true))) return rc;
-                if (slot_in_used[si]) GSF_CUDA(cudaEventSynchronize(sl.ev_h2d));
-                gather_pos(p, j0, cnt, sl.h_pos, host_threads);
-                GSF_CUDA(cudaMemcpyAsync(sl.d_pos, sl.h_pos, (size_t)p.dim * cnt * sizeof(double),
+                wait_for([&]() { return sg->in_staged(c); }, c);
+                GSF_CUDA(cudaMemcpyAsync(sl.d_pos, sg->in_slot(c), (size_t)p.dim * cnt * sizeof(double),
                                          cudaMemcpyHostToDevice, st));
-                GSF_CUDA(cudaEventRecord(sl.ev_h2d, st));
-                slot_in_used[si] = true;
+                GSF_CUDA(cudaEventRecord(d.ev_ring_in[(size_t)(c % sg->ring_in)], st));
             }
             d.h2d_bytes += (int64_t)p.dim * cnt * (int64_t)sizeof(double);
             kpos = sl.d_pos;
@@ -819,7 +779,7 @@ int run_shard(DeviceCtx &d, const Problem &p, int64_t j_beg, int64_t j_end, int 
         double *kout;
         int64_t kos0, kos1;
         if (out_dev) {
-            kout = p.out + j0 * p.os1;
+            kout = p.out + jc * p.os1;
             kos0 = p.os0;
             kos1 = p.os1;
         } else {
@@ -835,35 +795,36 @@ int run_shard(DeviceCtx &d, const Problem &p, int64_t j_beg, int64_t j_end, int 
         if (!out_dev) {
             if (lay.direct) {
                 if (nc == 1 || lay.aos) {
-                    GSF_CUDA(cudaMemcpyAsync(p.out + j0 * p.os1, sl.d_out, (size_t)nc * cnt * sizeof(double),
+                    GSF_CUDA(cudaMemcpyAsync(p.out + jc * p.os1, sl.d_out, (size_t)nc * cnt * sizeof(double),
                                              cudaMemcpyDeviceToHost, st));
                 } else {
                     for (int a = 0; a < nc; ++a)
-                        GSF_CUDA(cudaMemcpyAsync(p.out + a * p.os0 + j0, sl.d_out + (size_t)a * cnt,
+                        GSF_CUDA(cudaMemcpyAsync(p.out + a * p.os0 + jc, sl.d_out + (size_t)a * cnt,
                                                  (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, st));
                 }
             } else {
-                if ((rc = ensure_cap(&sl.h_out, &sl.h_out_cap, (size_t)nc * cnt, true))) return rc;
-                GSF_CUDA(cudaMemcpyAsync(sl.h_out, sl.d_out, (size_t)nc * cnt * sizeof(double),
+                // the ring slot must have been drained of the chunk that used it last
+                if (c >= sg->ring_out) wait_for([&]() { return sg->out_scattered(c - sg->ring_out); }, c + 1);
+                GSF_CUDA(cudaMemcpyAsync(sg->out_slot(c), sl.d_out, (size_t)nc * cnt * sizeof(double),
                                          cudaMemcpyDeviceToHost, st));
-                GSF_CUDA(cudaEventRecord(sl.ev_done, st));
-                pend[si] = {j0, cnt, true};
+                GSF_CUDA(cudaEventRecord(d.ev_ring_out[(size_t)(c % sg->ring_out)], st));
             }
             d.d2h_bytes += (int64_t)nc * cnt * (int64_t)sizeof(double);
         }
         d.chunks++;
+        issued = c + 1;
+        if (sg) poll();
     }
 
-    // drain in issue order
-    for (int64_t c = std::max<int64_t>(0, n_chunks - kSlots); c < n_chunks; ++c) {
-        const int si = (int)(c % kSlots);
-        if (pend[si].live) {
-            GSF_CUDA(cudaEventSynchronize(d.slot[si].ev_done));
-            scatter_out(p, lay, pend[si].j0, pend[si].cnt, d.slot[si].h_out, host_threads);
-            pend[si].live = false;
-        }
+    // drain: scatter the remaining output chunks as their copies land
+    if (stage_out) {
+        int64_t c_done = 0;
+        wait_for([&]() {
+            while (c_done < n_chunks && sg->out_scattered(c_done)) ++c_done;
+            return c_done == n_chunks;
+        }, n_chunks);
     }
-    for (int s = 0; s < kSlots; ++s) GSF_CUDA(cudaStreamSynchronize(d.slot[s].stream));
+    for (int s = 0; s < (n_chunks > 1 ? kSlots : 1); ++s) GSF_CUDA(cudaStreamSynchronize(d.slot[s].stream));
     d.ws_used = false;   // everything that read the workspace has finished
     guard.armed = false;
     return GSF_OK;
@@ -889,10 +850,17 @@ class PinnedPool {
         const size_t sz = (bytes + 65535) / 65536 * 65536;
         {
             std::lock_guard<std::mutex> l(mu_);
+            // Page-locked memory cannot be swapped: callers that keep many results alive (ensembles)
+            // must not pin the host down.  Beyond the cap the request is refused and the caller
+            // falls back to ordinary memory (the Python module: np.empty + staged D2H).
+            if (live_bytes_ + sz > live_cap())
+                return fail(GSF_ERR_ALLOC, "pinned pool: %zu bytes live, request of %zu exceeds GSF_PINNED_LIVE_MB",
+                            live_bytes_, sz);
             auto it = free_.lower_bound(sz);
-            if (it != free_.end() && it->first <= 2 * sz) {
+            if (it != free_.end() && it->first <= sz + sz / 4) {
                 *out = it->second;
                 live_[it->second] = it->first;
+                live_bytes_ += it->first;
                 cached_ -= it->first;
                 free_.erase(it);
                 return GSF_OK;
@@ -907,6 +875,7 @@ class PinnedPool {
         }
         std::lock_guard<std::mutex> l(mu_);
         live_[p] = sz;
+        live_bytes_ += sz;
         *out = p;
         return GSF_OK;
     }
@@ -919,6 +888,7 @@ class PinnedPool {
             if (it == live_.end()) return fail(GSF_ERR_ARG, "gsf_host_free: unknown pointer");
             sz = it->second;
             live_.erase(it);
+            live_bytes_ -= sz;
             if (cached_ + sz <= cap()) {
                 free_.emplace(sz, p);
                 cached_ += sz;
@@ -940,8 +910,21 @@ class PinnedPool {
     static size_t cap()
     {
         const char *e = getenv("GSF_PINNED_CACHE_MB");
-        return (size_t)(e && *e ? atoll(e) : 2048) << 20;
+        return (size_t)(e && *e ? atoll(e) : 1024) << 20;
     }
+    // live (handed-out) pinned bytes: GSF_PINNED_LIVE_MB, default min(4 GiB, physical RAM / 8)
+    static size_t live_cap()
+    {
+        static const size_t v = []() {
+            const char *e = getenv("GSF_PINNED_LIVE_MB");
+            if (e && *e) return (size_t)atoll(e) << 20;
+            const long pages = sysconf(_SC_PHYS_PAGES), psz = sysconf(_SC_PAGE_SIZE);
+            size_t ram8 = pages > 0 && psz > 0 ? (size_t)pages * (size_t)psz / 8 : (size_t)1 << 30;
+            return std::min<size_t>((size_t)4 << 30, ram8);
+        }();
+        return v;
+    }
+    size_t live_bytes_ = 0;
     std::mutex mu_;
     std::multimap<size_t, void *> free_;
     std::unordered_map<void *, size_t> live_;
@@ -1006,6 +989,8 @@ void collect_stats(const Problem &p, const std::vector<DeviceCtx *> &used, doubl
     s.pos_memory = pos_kind;
     s.out_memory = out_kind;
     s.grid_path = grid_path;
+    s.poly_degree = grid_path ? 0 : (p.dim > gsf::kMaxTemplateDim ? gsf::kHiDeg : p.deg);
+    s.fp64_slots = grid_path ? 0 : p.dim + gsf::cos_slots(s.poly_degree) + p.nc();
     s.n_devices = (int)used.size();
     c.last_devs.clear();
     for (DeviceCtx *d : used) {
@@ -1013,6 +998,7 @@ void collect_stats(const Problem &p, const std::vector<DeviceCtx *> &used, doubl
         s.d2h_bytes += d->d2h_bytes;
         s.kernel_launches += d->launches;
         s.n_chunks += d->chunks;
+        s.staging_threads = std::max(s.staging_threads, d->staging_threads);
         c.last_devs.push_back(d->dev);
     }
     s.kernel_ms = -1.0;   // resolved lazily in gsf_get_last_stats (needs event sync)
@@ -1064,9 +1050,40 @@ int run_host_call(Problem p, const GridSpec *grid)
         }
     }
 
+    p.deg = choose_degree(p);
+
     std::vector<int> devs = c.devices_explicit ? c.devices : default_devices();
     for (int id : devs)
         if (id < 0 || id >= ndev_visible) return fail(GSF_ERR_ARG, "configured device %d not visible (%d devices)", id, ndev_visible);
+    // Device-resident arguments may still be in production on one of the caller's streams, and the
+    // library works on its own non-blocking streams, which nothing orders after those: a blocking
+    // entry point therefore waits for all work queued on the owning device(s) first.  (The
+    // stream-ordered gsf_summate_on_stream takes the caller's stream instead and never syncs.)
+    {
+        int seen[8], n_seen = 0;
+        auto sync_owner = [&](const void *ptr) {
+            int k = 0, dv = -1;
+            if (!ptr) return;
+            classify(ptr, &k, &dv);
+            if (k != 2 || dv < 0) return;
+            for (int i = 0; i < n_seen; ++i)
+                if (seen[i] == dv) return;
+            if (n_seen < 8) seen[n_seen++] = dv;
+            int prev = 0;
+            cudaGetDevice(&prev);
+            if (cudaSetDevice(dv) == cudaSuccess) cudaDeviceSynchronize();
+            cudaSetDevice(prev);
+            cudaGetLastError();
+        };
+        if (pos_kind == 2) sync_owner(p.pos);
+        if (out_kind == 2) sync_owner(p.out);
+        if (p.N > 0) {
+            sync_owner(p.k);
+            sync_owner(p.z1);
+            sync_owner(p.z2);
+            if (p.kind == gsf::kFourier) sync_owner(p.sf);
+        }
+    }
     if (pos_kind == 2 || out_kind == 2) {
         // device-resident data: the work runs where the data lives ...
         const int dv = pos_kind == 2 ? pos_dev : out_dev;
@@ -1321,24 +1338,33 @@ int gsf_summate_on_stream(int kind, int dim, int64_t n_modes, int64_t n_points, 
         return fail(GSF_ERR_ARG, "gsf_summate_on_stream needs pos and out in device memory of one device");
     DeviceCtx *d;
     if ((rc = get_device_ctx(pd, &d))) return rc;
-    int prev = 0;
-    cudaGetDevice(&prev);
+    struct DeviceRestore {   // every return below leaves the caller's current device untouched
+        int prev = -1;
+        DeviceRestore() { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; }
+        ~DeviceRestore() { if (prev >= 0) cudaSetDevice(prev); }
+    } restore;
+    struct CacheGuard {      // a failed call must not leave "records valid" behind: they may never have been produced
+        DeviceCtx *d;
+        bool armed = true;
+        ~CacheGuard() { if (armed) { d->rec_valid = false; d->ws_used = false; } }
+    } cache_guard{d};
     GSF_CUDA(cudaSetDevice(pd));
     cudaStream_t st = (cudaStream_t)cuda_stream;
     reset_call_counters(*d);
+    p.deg = choose_degree(p);
     const auto t0 = std::chrono::steady_clock::now();
     if (d->ws_used) GSF_CUDA(cudaStreamWaitEvent(st, d->ev_ws, 0));
-    if ((rc = prepare_modes(*d, p, st))) return rc;
+    if ((rc = prepare_modes(*d, p, st, gsf::amp_factor(p.deg)))) return rc;
     int P, L;
     choose_variant(*d, p, p.M, false, &P, &L);
     if ((rc = launch_sum(*d, p, p.pos, p.ps0, p.ps1, p.out, p.os0, p.os1, p.M, st, P, L))) return rc;
     GSF_CUDA(cudaEventRecord(d->ev_ws, st));
     d->ws_used = true;
     d->chunks = 1;
+    cache_guard.armed = false;
     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     std::vector<DeviceCtx *> used(1, d);
     collect_stats(p, used, ms, P, L, 2, 2, 0);
-    if (prev != pd) cudaSetDevice(prev);
     return GSF_OK;
 }
 
@@ -1521,6 +1547,44 @@ int gsf_set_variant(int points_per_thread, int lanes_per_point)
         return fail(GSF_ERR_ARG, "no kernel variant P=%d L=%d", points_per_thread, lanes_per_point);
     c.force_p = points_per_thread;
     c.force_l = lanes_per_point;
+    return GSF_OK;
+}
+
+int gsf_set_poly_degree(int degree)
+{
+    Context &c = ctx();
+    std::lock_guard<std::mutex> lock(c.mu);
+    if (degree != 0 && degree != gsf::kHiDeg && degree != gsf::kFastDeg)
+        return fail(GSF_ERR_ARG, "polynomial degree must be 0 (automatic), %d or %d", gsf::kFastDeg, gsf::kHiDeg);
+    c.poly_degree = degree;
+    return GSF_OK;
+}
+
+int gsf_host_register(void *ptr, int64_t bytes)
+{
+    if (!ptr || bytes <= 0) return fail(GSF_ERR_ARG, "gsf_host_register: bad arguments");
+    if (device_count_raw() <= 0) return fail(GSF_ERR_NO_DEVICE, "no CUDA device available");
+    cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) {
+        cudaGetLastError();
+        return GSF_OK;
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(e == cudaErrorMemoryAllocation ? GSF_ERR_ALLOC : GSF_ERR_CUDA, "cudaHostRegister(%lld bytes) failed: %s",
+                    (long long)bytes, cudaGetErrorString(e));
+    }
+    return GSF_OK;
+}
+
+int gsf_host_unregister(void *ptr)
+{
+    if (!ptr) return GSF_OK;
+    cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(GSF_ERR_CUDA, "cudaHostUnregister failed: %s", cudaGetErrorString(e));
+    }
     return GSF_OK;
 }
 

@@ -29,7 +29,8 @@ import numpy as np
 __version__ = "1.1.0+b200.0"   # reference crate version (Cargo.toml:3) + local build tag
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libgsfield.so")
+# GSF_LIB: load another build of the same ABI (A/B measurements, e.g. csrc `make variants`)
+_LIB_PATH = os.environ.get("GSF_LIB") or os.path.join(_HERE, "libgsfield.so")
 
 _i64 = ctypes.c_int64
 _vp = ctypes.c_void_p
@@ -43,6 +44,8 @@ class GsfStats(ctypes.Structure):
         ("kernel_launches", ctypes.c_int32), ("n_devices", ctypes.c_int32), ("n_chunks", ctypes.c_int32),
         ("points_per_thread", ctypes.c_int32), ("lanes_per_point", ctypes.c_int32),
         ("pos_memory", ctypes.c_int32), ("out_memory", ctypes.c_int32), ("grid_path", ctypes.c_int32),
+        ("poly_degree", ctypes.c_int32), ("fp64_slots", ctypes.c_int32), ("staging_threads", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
     ]
 
     def as_dict(self):
@@ -98,6 +101,9 @@ def _load():
     L.gsf_set_chunk_points.argtypes = [_i64]
     L.gsf_set_variant.argtypes = [_int, _int]
     L.gsf_set_profiling.argtypes = [_int]
+    L.gsf_set_poly_degree.argtypes = [_int]
+    L.gsf_host_register.argtypes = [_vp, _i64]
+    L.gsf_host_unregister.argtypes = [_vp]
     L.gsf_get_last_stats.argtypes = [ctypes.POINTER(GsfStats)]
     L.gsf_dfma_peak.argtypes = [_int, ctypes.c_double, ctypes.POINTER(ctypes.c_double),
                                 ctypes.POINTER(ctypes.c_double)]
@@ -118,6 +124,7 @@ def _load():
     for name in ("gsf_summate", "gsf_summate_incompr", "gsf_summate_fourier", "gsf_summate_on_stream",
                  "gsf_summate_ex", "gsf_set_grid_detection",
                  "gsf_set_devices", "gsf_shard_bounds", "gsf_host_alloc", "gsf_host_free", "gsf_set_chunk_points", "gsf_set_variant", "gsf_set_profiling",
+                 "gsf_set_poly_degree", "gsf_host_register", "gsf_host_unregister",
                  "gsf_get_last_stats", "gsf_dfma_peak", "gsf_abi_version", "gsf_device_count",
                  "gsf_shutdown"):
         getattr(L, name).restype = _int
@@ -626,6 +633,49 @@ def set_variant(points_per_thread=0, lanes_per_point=0):
     rc = _load().gsf_set_variant(int(points_per_thread), int(lanes_per_point))
     if rc:
         _raise(rc)
+
+
+def set_poly_degree(degree=0):
+    """Degree of the cosine polynomial of the point x mode kernels: 0 automatic (6 below 2^27
+    point*modes, 5 above), or force 5 / 6.  See include/gsfield.h."""
+    rc = _load().gsf_set_poly_degree(int(degree))
+    if rc:
+        _raise(rc)
+
+
+class pinned:
+    """Page-lock a caller-owned numpy array for as long as the object lives (context manager):
+
+        with gstools_core.pinned(pos):
+            for z1, z2 in ensemble: field = gstools_core.summate(k, z1, z2, pos)
+
+    The GPU then reads `pos` in place instead of staging it through the library's pinned ring."""
+
+    def __init__(self, array):
+        if not isinstance(array, np.ndarray) or not (array.flags.c_contiguous or array.flags.f_contiguous):
+            raise TypeError("pinned(): a contiguous numpy array is required")
+        self._arr = array
+        rc = _load().gsf_host_register(array.ctypes.data, array.nbytes)
+        if rc:
+            _raise(rc)
+        self._live = True
+
+    def release(self):
+        if self._live:
+            self._live = False
+            _load().gsf_host_unregister(self._arr.ctypes.data)
+
+    def __enter__(self):
+        return self._arr
+
+    def __exit__(self, *exc):
+        self.release()
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
 
 
 def set_profiling(enabled=True):

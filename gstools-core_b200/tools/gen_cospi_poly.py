@@ -97,15 +97,16 @@ def hexd(x):
 
 
 def monic_variant(cu, nsamp=2500):
-    """V3: the same degree-6 minimax polynomial with the leading coefficient factored out,
+    """V3: the degree-len(cu)-1 minimax polynomial with the leading coefficient factored out,
     U(s) = c*Q(s), Q monic.  Then cos(pi r) = c^2 * (Q^2 - 1/c^2) and c^2 folds into the mode
     amplitude, so the first Horner step is a DADD (s + Q5) instead of a DFMA with TWO constant
     operands -- which ptxas can only issue with both constants in registers (3 register-file reads:
     3 cycles on B200 instead of 2).  Q_i = U_i/c, E = 1/c^2 and S = c^2 are rounded to binary64;
     a small ulp search over (Q0, E, S) picks the combination with the smallest measured error."""
     import math
-    c = cu[6]
-    D = [float(ci / c) for ci in cu[:6]]
+    deg = len(cu) - 1
+    c = cu[deg]
+    D = [float(ci / c) for ci in cu[:deg]]
     E, S = float(1 / (c * c)), float(c * c)
     rng = np.random.default_rng(0)
     rs = [float(x) for x in np.concatenate([rng.uniform(-0.5, 0.5, nsamp), [0.0, 0.5, -0.5, 0.25, 1e-9, 0.4999999]])]
@@ -120,8 +121,8 @@ def monic_variant(cu, nsamp=2500):
         out = []
         for r in rs:
             s = mp.mpf(float(mp.mpf(r) * mp.mpf(r)))          # DMUL
-            v = mp.mpf(float(s + mp.mpf(d[5])))                # DADD
-            for di in d[4::-1]:
+            v = mp.mpf(float(s + mp.mpf(d[deg - 1])))          # DADD
+            for di in d[deg - 2::-1]:
                 v = mp.mpf(float(v * s + mp.mpf(di)))          # DFMA
             out.append(v)
         return out
@@ -162,14 +163,23 @@ def main():
               % (mp.nstr(eu, 3), mp.nstr(wu, 3)))
     for i, c in enumerate(cu64):
         out.write("#define GSF_U%d %s  /* %.17g */\n" % (i, hexd(c), c))
-    w3, q64, e64, s64 = monic_variant(cu)
-    out.write("\n// V3: the same U with its leading coefficient factored out, U = c*Q, Q monic (Q6 = 1):\n")
+    out.write("\n// V3: U of degree DEG with its leading coefficient factored out, U = c*Q, Q monic:\n")
     out.write("//     cos(pi r) = S * (Q(s)^2 - E), E = 1/c^2, S = c^2 (folded into the mode amplitude).\n")
-    out.write("//     measured |cos(pi r)| error in binary64 arithmetic (DADD + 5 DFMA + DFMA) <= %s\n" % mp.nstr(w3, 3))
-    for i, c in enumerate(q64):
-        out.write("#define GSF_Q%d %s  /* %.17g */\n" % (i, hexd(c), c))
-    out.write("#define GSF_QE %s  /* %.17g */\n" % (hexd(e64), e64))
-    out.write("#define GSF_QS %s  /* %.17g */\n" % (hexd(s64), s64))
+    out.write("//     Evaluation: 1 DADD + (DEG-1) DFMA + 1 DFMA.  GSF_Q<DEG>_<i>, GSF_Q<DEG>_E, GSF_Q<DEG>_S.\n")
+    for deg in (4, 5, 6):
+        if deg == 6:
+            cud = cu
+            eud = eu
+        else:
+            cud, eud = remez(lambda s: mp.sqrt(2) * mp.cos(mp.pi / 2 * mp.sqrt(s)) if s > 0 else mp.sqrt(2),
+                             mp.mpf(0), quarter, deg)
+        w3, q64, e64, s64 = monic_variant(cud)
+        out.write("// degree %d: minimax |U - u| = %s ; measured |cos(pi r)| error in binary64 arithmetic <= %s\n"
+                  % (deg, mp.nstr(eud, 3), mp.nstr(w3, 3)))
+        for i, c in enumerate(q64):
+            out.write("#define GSF_Q%d_%d %s  /* %.17g */\n" % (deg, i, hexd(c), c))
+        out.write("#define GSF_Q%d_E %s  /* %.17g */\n" % (deg, hexd(e64), e64))
+        out.write("#define GSF_Q%d_S %s  /* %.17g */\n" % (deg, hexd(s64), s64))
     out.write("\n// V1: cos(pi r) = C(s), deg 8.\n")
     out.write("//     minimax |C - cos| = %s ; measured error in binary64 FMA arithmetic <= %s\n"
               % (mp.nstr(ec, 3), mp.nstr(wc, 3)))

@@ -17,6 +17,12 @@
  *   - `pos` and `out` may live in pageable host memory, pinned host memory or device memory; the
  *     library detects which (cudaPointerGetAttributes).  Host data is streamed through the GPU in
  *     chunks (H2D / kernel / D2H overlapped); device-resident data is processed in place.
+ *   - Device-resident arguments of the BLOCKING entry points (gsf_summate*, gsf_summate_ex,
+ *     gsf_krige): the library works on its own non-blocking streams, so it first waits for all
+ *     work queued on the owning device (cudaDeviceSynchronize) -- arrays still being produced on
+ *     one of the caller's streams are safe to pass.  gsf_summate_on_stream instead orders its work
+ *     on the stream the caller names and never synchronises: the arrays must be produced on that
+ *     stream (or be complete) -- the usual CUDA stream contract.
  *   - `num_threads` is accepted for signature compatibility with the reference (src/field.rs:42);
  *     it never affects results and only caps the host threads used for staging copies of
  *     pageable memory.  <= 0 means "default".
@@ -36,7 +42,7 @@
 extern "C" {
 #endif
 
-#define GSF_ABI_VERSION 1
+#define GSF_ABI_VERSION 2
 
 enum gsf_status {
     GSF_OK = 0,
@@ -70,6 +76,10 @@ typedef struct gsf_stats {
     int32_t pos_memory;     /* 0 pageable host, 1 pinned host, 2 device                                  */
     int32_t out_memory;
     int32_t grid_path;      /* 0 general kernel, 1 structured grid auto-detected, 2 structured grid requested */
+    int32_t poly_degree;    /* degree of the cosine polynomial the summation kernel used (0: grid path)  */
+    int32_t fp64_slots;     /* FP64-pipe instructions per point*mode of that kernel: dim + 5 + degree + nc */
+    int32_t staging_threads;/* host threads that staged pageable memory through the pinned rings         */
+    int32_t reserved;
 } gsf_stats;
 
 /* ---- the three reference functions ------------------------------------------------------- */
@@ -212,9 +222,18 @@ int gsf_device_count(void);
  * n == 0 restores the default: env GSF_DEVICES="0,1,.." if set, else device 0 only. */
 int gsf_set_devices(const int *device_ids, int n);
 /* Pinned (page-locked) host memory from a caching pool, for result arrays: a D2H into such a
- * buffer needs no staging copy.  gsf_host_free returns the block to the pool. */
+ * buffer needs no staging copy.  gsf_host_free returns the block to the pool.  Page-locked memory
+ * cannot be swapped, so the pool refuses (GSF_ERR_ALLOC) once the blocks handed out exceed
+ * GSF_PINNED_LIVE_MB (default min(4 GiB, RAM/8)); freed blocks are cached up to GSF_PINNED_CACHE_MB
+ * (default 1024). */
 int gsf_host_alloc(int64_t bytes, void **ptr);
 int gsf_host_free(void *ptr);
+/* Page-lock / unlock a caller-owned host range (cudaHostRegister): positions that are evaluated
+ * again and again (ensembles over one mesh) can then be read by the GPU in place, without the
+ * staging copy pageable memory needs.  Registering costs ~0.3 ms per MB once; the caller keeps the
+ * range allocated until gsf_host_unregister. */
+int gsf_host_register(void *ptr, int64_t bytes);
+int gsf_host_unregister(void *ptr);
 /* The contiguous point range [begin, end) that shard `shard` of `n_shards` owns -- the partition
  * the library uses across devices and bench.py uses across ranks (one process per GPU). */
 int gsf_shard_bounds(int64_t n_points, int n_shards, int shard, int64_t *begin, int64_t *end);
@@ -225,6 +244,11 @@ int gsf_set_chunk_points(int64_t chunk_points);
  * {2,4,8,16,32}; for dim 4..8: (1,1), (1,4), (1,32).  Anything else returns GSF_ERR_ARG (checked
  * against the dim-3 table here; a forced pair a later call's dim lacks falls back to the heuristic). */
 int gsf_set_variant(int points_per_thread, int lanes_per_point);
+/* Degree of the cosine polynomial in the point x mode kernels: 0 = automatic (6 for small problems,
+ * 5 -- one DFMA cheaper, |error| <= 2.2e-13 per term, measured <= 1e-12 sigma -- from 2^27
+ * point*modes), or 5 / 6 to force one.  One degree per call; never changes with chunking or sharding.
+ * Environment: GSF_POLY_DEGREE. */
+int gsf_set_poly_degree(int degree);
 /* Enable CUDA-event timing of the kernels (fills kernel_ms / prep_ms; adds event-sync overhead
  * only in gsf_get_last_stats). */
 int gsf_set_profiling(int enabled);

@@ -26,7 +26,7 @@ def test_exports_every_declared_symbol():
     lib = ctypes.CDLL(os.path.join(ROOT, "gstools-core_b200", "gstools_core", "libgsfield.so"))
     for n in sorted(names):
         assert hasattr(lib, n), "libgsfield.so does not export %s" % n
-    assert lib.gsf_abi_version() == 1
+    assert lib.gsf_abi_version() == 2
 
 
 def test_module_surface_matches_reference():

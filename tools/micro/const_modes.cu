@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(128) sum_const(gsf::SumArgs a, int n_modes)
     for (int p = 0; p < P; ++p)
 #pragma unroll
         for (int c = 0; c < NC; ++c) acc[p][c] = 0.0;
-    const PolyCoef coef = {a.coef[0], a.coef[1], a.coef[2], a.coef[3], a.coef[4], a.coef[5], a.coef[6]};
+    const PolyCoef coef = {{a.coef[0], a.coef[1], a.coef[2], a.coef[3], a.coef[4], a.coef[5], a.coef[6]}};
 #pragma unroll U
     for (int i = 0; i < n_modes; ++i) {
         const double *m = c_modes + i * R;
@@ -55,17 +55,17 @@ __global__ void __launch_bounds__(128) sum_const(gsf::SumArgs a, int n_modes)
             sq[p] = __dmul_rn(r, r);
         }
 #pragma unroll
-        for (int p = 0; p < P; ++p) u[p] = fma(coef.c6, sq[p], coef.c5);
+        for (int p = 0; p < P; ++p) u[p] = fma(coef.c[6], sq[p], coef.c[5]);
 #pragma unroll
-        for (int p = 0; p < P; ++p) u[p] = fma(u[p], sq[p], coef.c4);
+        for (int p = 0; p < P; ++p) u[p] = fma(u[p], sq[p], coef.c[4]);
 #pragma unroll
-        for (int p = 0; p < P; ++p) u[p] = fma(u[p], sq[p], coef.c3);
+        for (int p = 0; p < P; ++p) u[p] = fma(u[p], sq[p], coef.c[3]);
 #pragma unroll
-        for (int p = 0; p < P; ++p) u[p] = fma(u[p], sq[p], coef.c2);
+        for (int p = 0; p < P; ++p) u[p] = fma(u[p], sq[p], coef.c[2]);
 #pragma unroll
-        for (int p = 0; p < P; ++p) u[p] = fma(u[p], sq[p], coef.c1);
+        for (int p = 0; p < P; ++p) u[p] = fma(u[p], sq[p], coef.c[1]);
 #pragma unroll
-        for (int p = 0; p < P; ++p) u[p] = fma(u[p], sq[p], coef.c0);
+        for (int p = 0; p < P; ++p) u[p] = fma(u[p], sq[p], coef.c[0]);
 #pragma unroll
         for (int p = 0; p < P; ++p) {
             const double y = fma(u[p], u[p], -1.0);

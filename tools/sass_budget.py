@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Static issue-slot budget of the mode loop of gsf_sum_kernel<D,NC,P,1>, from SASS.
 
-Usage:  python tools/sass_budget.py <binary or .so> [D NC P]       (default 3 1 3)
+Usage:  python tools/sass_budget.py <binary or .so> [D NC P [DEG]]  (default 3 1 3 5)
         python tools/sass_budget.py <binary or .so> --kernel <mangled-name substring>
                                                     (instruction mix of any kernel's hottest loop)
 
@@ -50,9 +50,10 @@ def function_sass(path, mangled_substring):
     return lines
 
 
-def kernel_sass(path, d, nc, p):
+def kernel_sass(path, d, nc, p, deg=5):
+    """SASS of gsf_sum_kernel<D, NC, P, L=1, DEG> (DEG: polynomial degree, 5 = throughput, 6 = high)"""
     out = sass_dump(path)
-    name = "_ZN3gsf14gsf_sum_kernelILi%dELi%dELi%dELi1EEEvNS_7SumArgsE" % (d, nc, p)
+    name = "_ZN3gsf14gsf_sum_kernelILi%dELi%dELi%dELi1ELi%dEEEvNS_7SumArgsE" % (d, nc, p, deg)
     lines, on = [], False
     for ln in out.splitlines():
         if "Function :" in ln:
@@ -114,9 +115,9 @@ def sources(text):
     return res
 
 
-def analyze(path, d=3, nc=1, p=3):
+def analyze(path, d=3, nc=1, p=3, deg=5):
     """issue budget of the mode loop: dict(mix, fp64, other, three_register, cycles, pipe_frac, body_len)"""
-    body = hottest_loop(kernel_sass(path, d, nc, p))
+    body = hottest_loop(kernel_sass(path, d, nc, p, deg))
     mix = {}
     prev = None
     penalties = 0
@@ -180,8 +181,9 @@ def main():
         print("  mix: " + ", ".join("%s %d" % kv for kv in sorted(mix.items(), key=lambda kv: -kv[1])))
         return
     d, nc, p = (int(x) for x in sys.argv[2:5]) if len(sys.argv) >= 5 else (3, 1, 3)
-    r = analyze(path, d, nc, p)
-    print("%s  <D=%d NC=%d P=%d>  loop body: %d instructions" % (path, d, nc, p, r["body_len"]))
+    deg = int(sys.argv[5]) if len(sys.argv) >= 6 else 5
+    r = analyze(path, d, nc, p, deg)
+    print("%s  <D=%d NC=%d P=%d DEG=%d>  loop body: %d instructions" % (path, d, nc, p, deg, r["body_len"]))
     print("  mix: " + ", ".join("%s %d" % kv for kv in sorted(r["mix"].items(), key=lambda kv: -kv[1])))
     print("  FP64 %d (x2 cycles)  other %d  three-register FP64 %d  => %d cycles, FP64 pipe %.1f %%"
           % (r["fp64"], r["other"], r["three_register"], r["cycles"], 100.0 * r["pipe_frac"]))
