@@ -1,18 +1,25 @@
 #!/usr/bin/env python3
 """bench.py -- headline benchmark of the B200 field summation (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|...]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c5|c1..c4]
 
-A "step" is one pass of the hot path (field::summator) over one batch of synthetic input.  The
-default workload is BASELINE.json configs[1] (C2): 3-D Exponential covariance, 1000 modes x 10^6
-points (100^3 grid), per GPU.  Under torchrun (N > 1) every rank runs the same-sized shard on its
-own GPU with no data-path collective (the path is embarrassingly parallel over points): weak
-scaling, value = points*modes of all ranks / max-over-ranks time.
+A "step" is one pass of the hot path (field::summator) over the whole synthetic workload.  The
+default workload is the north star's scaling case, BASELINE.json configs[4] (C5): 3-D Exponential
+covariance, 10^4 modes x 10^8 points (1000 x 1000 x 100 grid), 10^12 point*modes per step.  The
+points are sharded contiguously over the N GPUs, one process per GPU, rank r taking
+gsf_shard_bounds(M, N, r) -- the split that replaces `Zip::from(pos.columns()).par_map_collect`
+(/root/reference/src/field.rs:53).  The path has no exchange step, so there is no data-path
+collective: STRONG scaling, value = total point*modes / max-over-ranks time.
 
-Two numbers per run:
-  value : kernel path, inputs already resident in HBM, CUDA events on the launching stream.
-  e2e   : the reference-facing call gstools_core.summate(...) with HOST buffers (pinned input,
-          host result), H2D and D2H inside the timed region.
+Numbers per run:
+  value : kernel path, the rank's shard already resident in HBM, CUDA events on the launching stream.
+  e2e   : the reference-facing call gstools_core.summate(...) on plain PAGEABLE numpy positions
+          (what GSTools passes, /root/reference/src/lib.rs:43-46), host result; H2D and D2H inside
+          the timed call.  `e2e.pinned_input` is the same call on page-locked positions.
+  in_process : (N > 1, rank 0) ONE gstools_core.summate call sharding over all N devices inside one
+          process (gsf_set_devices) -- the design the library ships -- with a parity flag against
+          the single-device result at every shard boundary.
+  c2    : configs[1] (1000 modes x 10^6 points), per rank, for the per-call overheads a small problem exposes.
 
 `--impl reference` times the reference algorithm's CPU restatement (oracle/, OpenMP over all host
 cores; the Rust crate itself cannot be built in this image -- no cargo/rustc) on a bounded sample
@@ -44,13 +51,14 @@ L2_BYTES = 126 * 1024 * 1024
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--workload", default="c5", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the number of points (debug)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the c2 / structured_grid / in_process blocks")
     return ap.parse_args()
 
 
@@ -60,6 +68,30 @@ def peak_file():
             return json.load(f)
     except Exception:
         return {}
+
+
+WORKLOADS = {
+    "c1": ("C1 field::summator 2D Gaussian, 100 modes x 1e4 points", "summate", 2, 100),
+    "c2": ("C2 field::summator 3D Exponential, 1000 modes x 1e6 points (100^3 grid)", "summate", 3, 1000),
+    "c3": ("C3 field::summator_incompr 3D, 1000 modes x 1e6 points (100^3 grid)", "summate_incompr", 3, 1000),
+    "c4": ("C4 field::summator_fourier 2D, 1e4 modes x 4096^2 points", "summate_fourier", 2, 10000),
+    "c5": ("C5 field::summator 3D Exponential, 1e4 modes x 1e8 points (1000x1000x100 grid)", "summate", 3, 10000),
+}
+
+
+def config_for(args, m_total):
+    """The workload description -- identical in the `ours` and `reference` arms."""
+    name, kind, d, n = WORKLOADS[args.workload]
+    nc = d if kind == "summate_incompr" else 1
+    per_rank_bytes = (d + nc) * 8 * m_total // max(1, args.gpus)
+    return {
+        "workload": name + (" [scaled x%g]" % args.scale if args.scale != 1.0 else ""),
+        "kind": kind, "dim": d, "modes": n, "points_total": m_total, "point_modes_total": n * m_total,
+        "sharding": "contiguous point shards, one per GPU, no collective (strong scaling: total work fixed)",
+        "l2": ("inputs larger than L2: every step streams %.0f MB of positions/results per GPU through a %d MB L2"
+               % (per_rank_bytes / 1e6, L2_BYTES >> 20)) if per_rank_bytes > 2 * L2_BYTES else
+              "input/output sets rotated so that no step re-reads L2-resident data",
+    }
 
 
 # ------------------------------------------------------------------------------------------------
@@ -80,7 +112,7 @@ class ClockSampler:
             os.close(fd)
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "25"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+                 "-lms", "50"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -129,29 +161,39 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
-def cpu_reference_rate(w, seconds, threads=None):
-    """Oracle (C restatement of the Rayon path) on a bounded point sample; returns (Gpm/s, info)."""
+def cpu_sample(cfg, scale, seconds, threads):
+    """A bounded, evenly strided point sample of the workload sized to ~`seconds` of CPU time.
+    Returns (oracle function, argument tuple, sample size, total points, modes)."""
     import oracle
     from gstools_core import workloads
 
+    # probe on a small shard to learn the rate, then build the sample from strided single points
+    probe = workloads.make(cfg, scale, point_range=lambda m: (0, min(m, max(threads * 64, 4096))))
+    fn = getattr(oracle, probe["kind"])
+    n, m = probe["n"], probe["m"]
+    t0 = time.perf_counter(); fn(*probe["args"], threads); dt = time.perf_counter() - t0
+    rate = probe["m_local"] * n / max(dt, 1e-9)
+    ms = int(min(m, max(probe["m_local"], rate * seconds / n)))
+    # evenly strided over the whole domain: a few hundred contiguous runs, so that the generator
+    # never has to materialise the full position array (2.4 GB for C5)
+    runs = int(min(ms, 512))
+    run_len = max(1, ms // runs)
+    starts = np.linspace(0, m - run_len, runs).astype(np.int64)
+    parts = [workloads.make(cfg, scale, point_range=(int(s), int(s) + run_len))["args"][-1] for s in starts]
+    pos = np.ascontiguousarray(np.concatenate(parts, axis=1))
+    return fn, probe["args"][:-1] + (pos,), pos.shape[1], m, n
+
+
+def cpu_reference_rate(cfg, scale, seconds, threads=None):
+    """Oracle (C restatement of the Rayon path) on a bounded point sample; returns (Gpm/s, info, sample)."""
     threads = threads or host_threads()
-    fn = getattr(oracle, w["kind"])
-    n, m = w["n"], w["m"]
-    # probe to size the sample
-    m0 = min(m, max(threads * 64, 4096))
-    idx = np.linspace(0, m - 1, m0).astype(np.int64)
-    sub = workloads.subset_points(w, idx)
-    t0 = time.perf_counter(); fn(*sub["args"], threads); dt = time.perf_counter() - t0
-    rate = m0 * n / max(dt, 1e-9)
-    ms = int(min(m, max(m0, rate * seconds / n)))
-    idx = np.linspace(0, m - 1, ms).astype(np.int64)
-    sub = workloads.subset_points(w, idx)
-    t0 = time.perf_counter(); fn(*sub["args"], threads); dt = time.perf_counter() - t0
+    fn, a, ms, m, n = cpu_sample(cfg, scale, seconds, threads)
+    t0 = time.perf_counter(); fn(*a, threads); dt = time.perf_counter() - t0
     gpm = ms * n / dt / 1e9
     info = {"value": gpm, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": "%d of %d points x %d modes (evenly strided), %.2f s; cost is linear in points"
-                      % (ms, m, n, dt)}
-    return gpm, info, (sub, ms, dt)
+            "sample": "%d of %d points x %d modes (512 evenly spaced runs of consecutive points), %.2f s; cost is "
+                      "linear in points" % (ms, m, n, dt)}
+    return gpm, info, (fn, a, ms, m, n)
 
 
 def run_reference(args):
@@ -159,46 +201,31 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import oracle
-    from gstools_core import workloads
-
-    w = workloads.make(args.workload, args.scale)
     threads = host_threads()
     steps = max(1, args.steps)
     warm = max(0, args.warmup)
     # bounded sample per step: the whole run (warm-up + K steps) is sized to ~2 minutes of CPU time
     per_step = max(0.05, min(20.0, 120.0 / (steps + warm)))
-    _, info, (sub, ms, _dt) = cpu_reference_rate(w, per_step, threads)
-    fn = getattr(oracle, w["kind"])
+    _, info, (fn, a, ms, m, n) = cpu_reference_rate(args.workload, args.scale, per_step, threads)
     for _ in range(warm):
-        fn(*sub["args"], threads)
+        fn(*a, threads)
     t0 = time.perf_counter()
     for _ in range(steps):
-        fn(*sub["args"], threads)
+        fn(*a, threads)
     dt = (time.perf_counter() - t0) / steps
-    gpm = ms * w["n"] / dt / 1e9
-    info.update(value=gpm, sample="%d of %d points x %d modes per step (evenly strided); linear in points"
-                % (ms, w["m"], w["n"]))
+    gpm = ms * n / dt / 1e9
+    info.update(value=gpm, sample="%d of %d points x %d modes per step (512 evenly spaced runs of consecutive points); "
+                "cost is linear in points; ms_per_step is extrapolated to the full point count" % (ms, m, n))
     line = {
         "impl": "reference", "metric": METRIC, "value": gpm, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3 * (w["m"] / ms), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.workload), "note": "ms_per_step extrapolated to the full point count"},
+        "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3 * (m / ms), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_for(args, m),
         "cpu_baseline": info,
         "e2e": {"value": gpm, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
-
-
-def workload_name(c):
-    return {
-        "c1": "C1 field::summator 2D Gaussian, 100 modes x 1e4 points",
-        "c2": "C2 field::summator 3D Exponential, 1000 modes x 1e6 points (100^3 grid) per GPU",
-        "c3": "C3 field::summator_incompr 3D, 1000 modes x 1e6 points per GPU",
-        "c4": "C4 field::summator_fourier 2D, 1e4 modes x 4096^2 points per GPU",
-        "c5": "C5 field::summator 3D, 1e4 modes x 1e8 points per GPU",
-    }[c]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -216,8 +243,10 @@ def run_ours(args):
         raise RuntimeError("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local)
     gc.set_devices([local])
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        cpu_group = dist.new_group(backend="gloo")   # host-side barrier for the phases that must leave the GPUs idle
 
     def barrier():
         if world > 1:
@@ -231,23 +260,24 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    w = workloads.make(args.workload, args.scale)
-    kind, n, m, d = w["kind"], w["n"], w["m"], w["d"]
-    pm = n * m
-    nc = d if kind == "summate_incompr" else 1
     W, K = max(args.warmup, 3), max(args.steps, 1)
-
-    # ---- device-resident inputs: rotate over enough copies that a step's input was evicted from
-    # L2 by the time it is reused (sets * (pos + out) > L2)
-    pos_bytes, out_bytes = d * m * 8, nc * m * 8
-    n_sets = max(2, -(-2 * L2_BYTES // (pos_bytes + out_bytes)))
-    n_sets = min(n_sets, 16)
-    l2_note = ("rotating %d input/output sets (%.0f MB > 126 MB L2) so no step re-reads L2-resident data"
-               % (n_sets, n_sets * (pos_bytes + out_bytes) / 1e6)) if n_sets * (pos_bytes + out_bytes) > L2_BYTES else (
-        "rotating %d input/output sets (%.1f MB in total: this workload is smaller than L2 and launch-latency bound)"
-        % (n_sets, n_sets * (pos_bytes + out_bytes) / 1e6))
+    shard = lambda m: gc.shard_bounds(m, world, rank)                       # noqa: E731
+    w = workloads.make(args.workload, args.scale, point_range=shard if world > 1 else None)
+    kind, n, m_total, m, d = w["kind"], w["n"], w["m"], w["m_local"], w["d"]
+    pm_total, pm_local = n * m_total, n * m
+    nc = d if kind == "summate_incompr" else 1
     margs = w["args"][:-1]
-    pos_host = w["args"][-1]
+    pos_host = w["args"][-1]                                                  # plain numpy: pageable
+
+    # The headline numbers measure the GENERAL point x mode kernel: the positions happen to be a
+    # grid, which the default API would detect and route to the structured-grid GEMM path -- that
+    # path is measured separately below ("structured_grid").
+    gc.set_grid_detection(False)
+    gc.set_profiling(False)
+
+    # ---- value: device-resident shard.  Sets are rotated unless one set already exceeds 2x L2.
+    pos_bytes, out_bytes = d * m * 8, nc * m * 8
+    n_sets = 1 if pos_bytes + out_bytes > 2 * L2_BYTES else min(16, max(2, -(-2 * L2_BYTES // (pos_bytes + out_bytes))))
     dev_modes = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in margs]
     dev_pos = [torch.from_numpy(pos_host).cuda() for _ in range(n_sets)]
     oshape = (m, nc) if nc > 1 else (m,)
@@ -259,11 +289,6 @@ def run_ours(args):
         o = dev_out[i % n_sets]
         dev_fn(*dev_modes, dev_pos[i % n_sets], o.t() if nc > 1 else o, stream=stream.cuda_stream)
 
-    # The headline numbers measure the GENERAL point x mode kernel: C2's positions happen to be a
-    # grid, which the default API would detect and route to the structured-grid GEMM path -- that
-    # path is measured separately below ("structured_grid").
-    gc.set_grid_detection(False)
-    gc.set_profiling(False)
     sampler = ClockSampler(local)
     if rank == 0 and os.environ.get("GSF_BENCH_NO_SAMPLER") != "1":
         sampler.start()
@@ -271,120 +296,95 @@ def run_ours(args):
     for i in range(W):
         dev_step(i)
     barrier()
-    launches = 0
+    # kernel time and step time come from ONE loop: the library records its own CUDA events around
+    # every summation kernel on the launching stream (profiling mode 2 = accumulate over calls)
+    gc.set_profiling(2)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
     for i in range(K):
         dev_step(i)
-        launches += gc.last_stats()["kernel_launches"]
     e1.record(stream)
     barrier()
     dev_ms = max_over_ranks(e0.elapsed_time(e1)) / K
-    variant = gc.last_stats()
-    # The sampler covers the device-timed region only: nvidia-smi polling takes driver locks and
-    # visibly disturbs the host-synchronous end-to-end calls measured below (750-950 G pm/s with the
-    # poller running vs a stable ~980 without, tools/e2e_probe.py).
-    clocks = sampler.stop() if rank == 0 else {}
-
-    # ---- dominant kernel alone: library-side CUDA events on the launching stream, per launch
-    gc.set_profiling(True)
-    kms = []
-    for i in range(min(K, 20)):
-        dev_step(i)
-        torch.cuda.synchronize()
-        kms.append(gc.last_stats()["kernel_ms"])
+    variant = gc.last_stats()                      # kernel_ms: summed over the K calls (accumulate mode)
+    launches = K * variant["kernel_launches"]      # per call: gsf_prep_modes + gsf_sum_kernel
+    kernel_ms = max_over_ranks(variant["kernel_ms"]) / K
     gc.set_profiling(False)
-    kernel_ms = statistics.mean(kms)
+    # The sampler covers the device-timed region only: nvidia-smi polling takes driver locks and
+    # visibly disturbs the host-synchronous end-to-end calls measured below.
+    clocks = sampler.stop() if rank == 0 else {}
+    del dev_pos
+    torch.cuda.empty_cache()
 
-    # ---- end to end through the reference-facing API: pinned host input, host result
+    # ---- e2e: the reference-facing API on PAGEABLE host positions, host result
     host_fn = getattr(gc, kind)
-    pin = [torch.from_numpy(pos_host).pin_memory() for _ in range(2)]
-    pin_np = [p.numpy() for p in pin]
-    for i in range(W):
-        host_fn(*margs, pin_np[i % 2])
-    barrier()
-    # K host-synchronous calls, repeated three times; the MEDIAN repetition is reported (all three
-    # are listed): this loop runs on the host's clock and a noisy neighbour on the shared box moves
-    # a single repetition by +-10 %.
+    step_s = dev_ms * 1e-3
+    Ke = K if step_s < 0.2 else max(3, min(K, 10))
+    pages = [pos_host] if pos_bytes > (512 << 20) else [pos_host, pos_host.copy()]
+
     e2e_launches = 0
+
+    def timed_calls(fn, arrays, k, warm):
+        nonlocal e2e_launches
+        for i in range(warm):
+            fn(*margs, arrays[i % len(arrays)])
+        barrier()
+        t0 = time.perf_counter()
+        res = None
+        for i in range(k):
+            res = fn(*margs, arrays[i % len(arrays)])
+        torch.cuda.synchronize()
+        local_ms = (time.perf_counter() - t0) * 1e3
+        barrier()
+        e2e_launches += k * gc.last_stats()["kernel_launches"]
+        return max_over_ranks(local_ms) / k, res
+
+    # short steps run on the host's clock and a noisy neighbour moves one repetition by +-10 %:
+    # three repetitions, the median is reported (all three are listed); long steps need one
     reps = []
-    for rep in range(3):
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(K):
-            res = host_fn(*margs, pin_np[i % 2])
-            e2e_launches += gc.last_stats()["kernel_launches"]
-        torch.cuda.synchronize()
-        e2e_local = (time.perf_counter() - t0) * 1e3
-        barrier()
-        reps.append(max_over_ranks(e2e_local) / K)
+    res = None
+    for rep in range(3 if step_s < 0.05 else 1):
+        ms_rep, res = timed_calls(host_fn, pages, Ke, min(W, 3) if rep == 0 else 0)
+        reps.append(ms_rep)
+    e2e_ms = sorted(reps)[len(reps) // 2]
     st = gc.last_stats()
-    e2e_ms = sorted(reps)[1]
     checksum = float(res.sum())
+    del res
 
-    # ---- same call from PAGEABLE host memory (plain numpy arrays, what GSTools passes today):
-    # the library stages through its pinned ring; bounded by one host memcpy pass over the input
-    for i in range(W):
-        host_fn(*margs, pos_host)
-    barrier()
-    Kp = max(1, min(K, 50))
-    t0 = time.perf_counter()
-    for i in range(Kp):
-        resp = host_fn(*margs, pos_host)
-    torch.cuda.synchronize()
-    pg_local = (time.perf_counter() - t0) * 1e3
-    barrier()
-    e2e_pageable_ms = max_over_ranks(pg_local) / Kp
+    # same call with the positions page-locked by the caller (gstools_core.pinned): the GPU reads them in place
+    Kp = Ke if step_s < 0.2 else max(2, min(Ke, 5))
+    pin_h = gc.pinned(pages[0])
+    e2e_pinned_ms, _ = timed_calls(host_fn, pages[:1], Kp, 2)
+    st_pin = gc.last_stats()
+    pin_h.release()
 
-    # ---- structured-grid path, reported separately: different algorithmic work
+    # ---- c2 block: configs[1] per rank (1000 modes x 1e6 points): per-call overheads
+    c2 = None
+    if not args.no_extras and args.scale == 1.0:
+        c2 = c2_block(gc, workloads, torch, timed_calls_factory=(barrier, max_over_ranks), world=world)
+
+    # ---- structured-grid path of the default API (different algorithmic work: reported separately)
     grid = None
-    if w.get("axes") is not None:
-        gc.set_grid_detection(True)
-        for i in range(W):
-            host_fn(*margs, pin_np[i % 2])
-        assert gc.last_stats()["grid_path"] == 1
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(K):
-            resg = host_fn(*margs, pin_np[i % 2])
-        torch.cuda.synchronize()
-        g_e2e_local = (time.perf_counter() - t0) * 1e3
-        barrier()
-        g_e2e_ms = max_over_ranks(g_e2e_local) / K
-        # kernel path: explicit axes, device-resident result, library CUDA events around the GEMM
-        grid_fn = getattr(gc, kind + "_grid")
-        gout = dev_out[0].t() if nc > 1 else dev_out[0]
-        gc.set_profiling(True)
-        gk = []
-        for i in range(W + min(K, 20)):
-            grid_fn(*margs, w["axes"], out=gout)
-            torch.cuda.synchronize()
-            if i >= W:
-                gk.append(gc.last_stats()["kernel_ms"])
-        gc.set_profiling(False)
-        g_kernel_ms = statistics.mean(gk)
-        dmma_rate, dmma_ms = gc.dmma_peak(local, 300.0)
-        fma_per_pm = 2 * nc
-        grid = {
-            "note": "points form a rectilinear grid: the sum factorises per axis into an FP64 GEMM "
-                    "(2*NC FMA per point*mode + O(1/n_last)); same results within 1e-9 sigma",
-            "e2e": {"value": world * pm / (g_e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": g_e2e_ms,
-                    "api": "gstools_core.%s(host arrays) with automatic exact grid detection (default)" % kind},
-            "kernel": {"value": pm / (g_kernel_ms * 1e-3) / 1e9, "unit": UNIT, "kernel_ms": g_kernel_ms,
-                       "name": "gsf_grid_gemm (DMMA.8x8x4)"},
-            "roofline": {"bound": "fp64 tensor", "achieved": pm * fma_per_pm * 2 / (g_kernel_ms * 1e-3) / 1e12,
-                         "peak": dmma_rate * 2 / 1e12, "unit": "TFLOP/s",
-                         "frac": pm * fma_per_pm / (g_kernel_ms * 1e-3) / dmma_rate,
-                         "fma_per_point_mode": fma_per_pm,
-                         "peak_source": "gsf_dmma_peak measured in this run: %.2f T FMA/s over %.0f ms (of measured)"
-                                        % (dmma_rate / 1e12, dmma_ms)},
-            "max_abs_diff_vs_general_over_sigma": float(np.max(np.abs(resg - res)) / np.std(res)),
-        }
+    if world == 1 and w.get("axes") is not None and not args.no_extras:
+        grid = grid_block(gc, torch, kind, margs, pos_host, w["axes"], nc, m, pm_local, W, 5 if step_s > 0.2 else K, local)
         gc.set_grid_detection(False)
 
     # ---- roofline denominator: measured DFMA issue rate (same box, same run)
     dfma_rate, dfma_ms = gc.dfma_peak(local, 300.0)
+
+    # ---- in-process multi-device call (rank 0 drives all N GPUs; the other ranks wait on the host)
+    inproc = None
+    if world > 1 and not args.no_extras:
+        torch.cuda.synchronize()
+        dist.barrier(group=cpu_group)
+        if rank == 0:
+            try:
+                inproc = in_process_block(gc, workloads, args, world)
+            except Exception as exc:   # never lose the headline line over the extra block
+                inproc = {"error": "%s: %s" % (type(exc).__name__, exc)}
+            gc.set_devices([local])
+        dist.barrier(group=cpu_group)
 
     if rank != 0:
         if world > 1:
@@ -393,66 +393,240 @@ def run_ours(args):
 
     peaks = peak_file()
     traffic = None
-    if args.workload == "c2" and args.scale == 1.0:
-        try:   # DRAM bytes per launch from the committed ncu --set full capture of this kernel
-            with open(os.path.join(ROOT, "profiles", "ncu_r1_c2_traffic.json")) as f:
-                t = json.load(f)
+    try:   # DRAM bytes per launch from the committed ncu --set full capture of this kernel / workload
+        with open(os.path.join(ROOT, "profiles", "ncu_r2_%s_traffic.json" % args.workload)) as f:
+            t = json.load(f)
+        if world == 1 and args.scale == 1.0:
             traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
-        except Exception:
-            traffic = None
-    w_exec = workloads.W_EXEC[args.workload]
-    w_survey = workloads.W_SURVEY[args.workload]
-    pm_per_s_kernel = pm / (kernel_ms * 1e-3)
+    except Exception:
+        traffic = None
+    w_exec = variant["fp64_slots"]
+    pm_per_s_kernel = pm_local / (kernel_ms * 1e-3)
     ach_tflops = pm_per_s_kernel * w_exec * 2 / 1e12
     peak_tflops = dfma_rate * 2 / 1e12
     line = {
-        "metric": METRIC, "value": world * pm / (dev_ms * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world,
-        "steps": K, "warmup": W, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak",
+        "metric": METRIC, "value": pm_total / (dev_ms * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world,
+        "steps": K, "warmup": W, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {
-            "workload": workload_name(args.workload), "kind": kind, "dim": d, "modes": n,
-            "points_per_gpu": m, "point_modes_per_gpu": pm,
-            "l2": l2_note,
-            "kernel_variant": {"points_per_thread": variant["points_per_thread"],
-                               "lanes_per_point": variant["lanes_per_point"]},
-            "grid_detection": "off for value / e2e / roofline (general point x mode kernel); the default "
-                              "behaviour on this gridded input is reported under structured_grid",
-        },
-        "e2e": {"value": world * pm / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_ms,
+        "config": config_for(args, m_total),
+        "e2e": {"value": pm_total / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_ms, "steps": Ke,
                 "h2d_bytes_per_step": st["h2d_bytes"], "d2h_bytes_per_step": st["d2h_bytes"],
-                "api": "gstools_core.%s(host arrays; pos pinned, result in a host ndarray)" % kind,
-                "chunks_per_step": st["n_chunks"], "checksum": checksum,
-                "repetitions_ms_per_step": reps, "reported": "median of 3 repetitions of K steps",
-                "transfer": ("zero-copy: one launch reads the pinned positions and writes the pinned result over "
-                             "PCIe inside the timed call (no separate cudaMemcpy)" if st["n_chunks"] == 1 and
-                             os.environ.get("GSF_ZERO_COPY", "1") != "0" else "chunked H2D / kernel / D2H pipeline"),
-                "pageable_input": {"value": world * pm / (e2e_pageable_ms * 1e-3) / 1e9, "unit": UNIT,
-                                   "ms_per_step": e2e_pageable_ms, "steps": Kp,
-                                   "note": "same call on plain (pageable) numpy positions"}},
+                "api": "gstools_core.%s(plain pageable numpy arrays) -> host ndarray, one call per rank on its shard" % kind,
+                "chunks_per_step": st["n_chunks"], "staging_threads": st["staging_threads"], "checksum": checksum,
+                "repetitions_ms_per_step": reps,
+                "transfer": "pageable positions staged through a pinned ring by the library's host crew, chunked "
+                            "H2D / kernel / D2H pipeline; result lands in a pinned-pool ndarray",
+                "pinned_input": {"value": pm_total / (e2e_pinned_ms * 1e-3) / 1e9, "unit": UNIT,
+                                 "ms_per_step": e2e_pinned_ms, "steps": Kp, "chunks_per_step": st_pin["n_chunks"],
+                                 "note": "same call, positions page-locked by the caller (gstools_core.pinned)"}},
         "gpu_launches": launches + e2e_launches,
         "roofline": {
             "bound": "fp64", "achieved": ach_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
             "frac": ach_tflops / peak_tflops, "traffic": traffic,
             "traffic_unit": "bytes of DRAM per launch (ncu dram__bytes_read+write); algorithmic bytes: %d" % (pos_bytes + out_bytes),
-            "kernel": "gsf_sum_kernel", "kernel_ms": kernel_ms,
-            "fp64_slots_per_point_mode": w_exec,
+            "kernel": "gsf_sum_kernel<D=%d,NC=%d,P=%d,L=%d,DEG=%d>" % (d, nc, variant["points_per_thread"],
+                                                                      variant["lanes_per_point"], variant["poly_degree"]),
+            "kernel_ms": kernel_ms, "timed": "library CUDA events around every launch, same loop as ms_per_step",
+            "fp64_slots_per_point_mode": w_exec, "poly_degree": variant["poly_degree"],
             "peak_source": "gsf_dfma_peak measured in this run: %.2f T DFMA/s over %.0f ms (of measured)"
                            % (dfma_rate / 1e12, dfma_ms),
-            "frac_at_survey_work": pm_per_s_kernel * w_survey / dfma_rate,
-            "survey_slots_per_point_mode": w_survey,
+            "survey_slots_per_point_mode": workloads.W_SURVEY[args.workload],
             "hbm_gbs_needed": (pos_bytes + out_bytes) / (kernel_ms * 1e-3) / 1e9,
             "hbm_gbs_measured_peak": peaks.get("hbm_gbs"),
         },
         "clocks": clocks,
+        "detail": {
+            "points_per_gpu": m, "point_modes_per_gpu": pm_local,
+            "device_sets": n_sets,
+            "grid_detection": "off for value / e2e / roofline (general point x mode kernel); the default behaviour "
+                              "on this gridded input is reported under structured_grid / in_process.default_api",
+        },
     }
+    if c2 is not None:
+        line["c2"] = c2
     if grid is not None:
         line["structured_grid"] = grid
+    if inproc is not None:
+        line["in_process"] = inproc
     if world == 1 and not args.no_cpu_baseline:
-        _, info, _ = cpu_reference_rate(w, args.cpu_seconds)
+        _, info, _ = cpu_reference_rate(args.workload, args.scale, args.cpu_seconds)
         line["cpu_baseline"] = info
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def c2_block(gc, workloads, torch, timed_calls_factory, world):
+    """configs[1] on every rank at once (weak): device-timed kernel, pageable and pinned e2e."""
+    barrier, max_over_ranks = timed_calls_factory
+    w = workloads.make("c2")
+    k, z1, z2, pos = w["args"]
+    pm = w["n"] * w["m"]
+    dk, dz1, dz2 = (torch.from_numpy(a).cuda() for a in (k, z1, z2))
+    sets = 9
+    dpos = [torch.from_numpy(pos).cuda() for _ in range(sets)]
+    dout = [torch.empty(w["m"], dtype=torch.float64, device="cuda") for _ in range(sets)]
+    stream = torch.cuda.current_stream()
+    gc.set_grid_detection(False)
+    for i in range(5):
+        gc.summate_device(dk, dz1, dz2, dpos[i % sets], dout[i % sets], stream=stream.cuda_stream)
+    barrier()
+    gc.set_profiling(2)
+    K = 100
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(K):
+        gc.summate_device(dk, dz1, dz2, dpos[i % sets], dout[i % sets], stream=stream.cuda_stream)
+    e1.record(stream)
+    barrier()
+    dev_ms = max_over_ranks(e0.elapsed_time(e1)) / K
+    stv = gc.last_stats()
+    kernel_ms = max_over_ranks(stv["kernel_ms"]) / K
+    gc.set_profiling(False)
+    del dpos, dout
+
+    def host_ms(arrays, k_steps):
+        for i in range(5):
+            gc.summate(k, z1, z2, arrays[i % len(arrays)])
+        reps = []
+        for _ in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(k_steps):
+                gc.summate(k, z1, z2, arrays[i % len(arrays)])
+            reps.append(max_over_ranks((time.perf_counter() - t0) * 1e3) / k_steps)
+        return sorted(reps)[1], reps
+
+    pages = [pos, pos.copy()]
+    page_ms, page_reps = host_ms(pages, 50)
+    st = gc.last_stats()
+    h0, h1 = gc.pinned(pages[0]), gc.pinned(pages[1])
+    pin_ms, pin_reps = host_ms(pages, 50)
+    h0.release(); h1.release()
+    out = {
+        "workload": WORKLOADS["c2"][0] + " per rank (weak)",
+        "kernel": {"value": world * pm / (dev_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": dev_ms, "kernel_ms": kernel_ms,
+                   "poly_degree": stv["poly_degree"], "fp64_slots_per_point_mode": stv["fp64_slots"]},
+        "e2e_pageable": {"value": world * pm / (page_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": page_ms,
+                         "repetitions_ms_per_step": page_reps, "chunks_per_step": st["n_chunks"],
+                         "staging_threads": st["staging_threads"]},
+        "e2e_pinned": {"value": world * pm / (pin_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": pin_ms,
+                       "repetitions_ms_per_step": pin_reps},
+    }
+    if world == 1:
+        # default API on this gridded input (exact grid detection on): the structured-grid GEMM path
+        gc.set_grid_detection(True)
+        for i in range(5):
+            gc.summate(k, z1, z2, pages[i % 2])
+        gp = gc.last_stats()["grid_path"]
+        t0 = time.perf_counter()
+        for i in range(50):
+            gc.summate(k, z1, z2, pages[i % 2])
+        out["default_api_grid_path"] = {"ms_per_step": (time.perf_counter() - t0) * 1e3 / 50, "grid_path": gp,
+                                        "note": "gstools_core.summate(pageable pos), detection on"}
+        gc.set_grid_detection(False)
+    return out
+
+
+def grid_block(gc, torch, kind, margs, pos_host, axes, nc, m, pm, W, K, local):
+    host_fn = getattr(gc, kind)
+    gc.set_grid_detection(True)
+    for i in range(min(W, 2)):
+        resg = host_fn(*margs, pos_host)
+    assert gc.last_stats()["grid_path"] == 1
+    t0 = time.perf_counter()
+    for i in range(K):
+        resg = host_fn(*margs, pos_host)
+    torch.cuda.synchronize()
+    g_e2e_ms = (time.perf_counter() - t0) * 1e3 / K
+    del resg
+    # kernel path: explicit axes, device-resident result, library CUDA events around the GEMM
+    grid_fn = getattr(gc, kind + "_grid")
+    gout = torch.empty((m, nc) if nc > 1 else (m,), dtype=torch.float64, device="cuda")
+    gout = gout.t() if nc > 1 else gout
+    gc.set_profiling(True)
+    gk = []
+    for i in range(2 + min(K, 10)):
+        grid_fn(*margs, axes, out=gout)
+        torch.cuda.synchronize()
+        if i >= 2:
+            gk.append(gc.last_stats()["kernel_ms"])
+    gc.set_profiling(False)
+    g_kernel_ms = statistics.mean(gk)
+    dmma_rate, dmma_ms = gc.dmma_peak(local, 300.0)
+    fma_per_pm = 2 * nc
+    return {
+        "note": "points form a rectilinear grid: the sum factorises per axis into an FP64 GEMM "
+                "(2*NC FMA per point*mode + O(1/n_last)); same results within 1e-9 sigma",
+        "e2e": {"value": pm / (g_e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": g_e2e_ms,
+                "api": "gstools_core.%s(pageable host arrays) with automatic exact grid detection (default)" % kind},
+        "kernel": {"value": pm / (g_kernel_ms * 1e-3) / 1e9, "unit": UNIT, "kernel_ms": g_kernel_ms,
+                   "name": "gsf_grid_gemm (DMMA.8x8x4)"},
+        "roofline": {"bound": "fp64 tensor", "achieved": pm * fma_per_pm * 2 / (g_kernel_ms * 1e-3) / 1e12,
+                     "peak": dmma_rate * 2 / 1e12, "unit": "TFLOP/s",
+                     "frac": pm * fma_per_pm / (g_kernel_ms * 1e-3) / dmma_rate,
+                     "fma_per_point_mode": fma_per_pm,
+                     "peak_source": "gsf_dmma_peak measured in this run: %.2f T FMA/s over %.0f ms (of measured)"
+                                    % (dmma_rate / 1e12, dmma_ms)},
+    }
+
+
+def in_process_block(gc, workloads, args, world):
+    """ONE gstools_core call on rank 0 sharding the whole workload over all `world` devices inside
+    the process (gsf_set_devices; one host thread + staging crew per device), from pageable memory;
+    parity against the single-device result at every shard boundary."""
+    w = workloads.make(args.workload, args.scale)
+    kind, n, m = w["kind"], w["n"], w["m"]
+    fn = getattr(gc, kind)
+    a = w["args"]
+    gc.set_grid_detection(False)
+    gc.set_devices(list(range(world)))
+    fn(*a)                                            # warm-up (allocates the per-device rings)
+    times = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        many = fn(*a)
+        times.append((time.perf_counter() - t0) * 1e3)
+    stm = gc.last_stats()
+    # parity: 1024 points either side of every shard boundary + first/last 1024 + a strided sample,
+    # recomputed on ONE device with the same polynomial degree; the per-point mode order does not
+    # depend on the shard, so the results must be bit-identical
+    idx = [np.arange(0, min(m, 1024)), np.arange(max(0, m - 1024), m), np.arange(0, m, max(1, m // 65536))]
+    for r in range(1, world):
+        b, _ = gc.shard_bounds(m, world, r)
+        idx.append(np.arange(max(0, b - 1024), min(m, b + 1024)))
+    idx = np.unique(np.concatenate(idx))
+    sub = list(a)
+    sub[-1] = np.ascontiguousarray(a[-1][:, idx])
+    gc.set_devices([0])
+    gc.set_poly_degree(stm["poly_degree"])
+    one = fn(*sub)
+    gc.set_poly_degree(0)
+    got = many[:, idx] if many.ndim == 2 else many[idx]
+    parity = bool(np.array_equal(got, one))
+    max_diff = float(np.max(np.abs(got - one)))
+    del many
+    out = {
+        "api": "one gstools_core.%s(pageable host arrays) call, gsf_set_devices(range(%d))" % (kind, world),
+        "value": n * m / (min(times) * 1e-3) / 1e9, "unit": UNIT, "ms_per_call_min": min(times), "ms_per_call": times,
+        "n_devices": stm["n_devices"], "chunks": stm["n_chunks"], "poly_degree": stm["poly_degree"],
+        "parity_bit_identical_to_one_device": parity, "parity_points": int(idx.size), "max_abs_diff": max_diff,
+    }
+    if w.get("axes") is not None:
+        # what the default API does on this gridded input across the devices (structured-grid path)
+        gc.set_devices(list(range(world)))
+        gc.set_grid_detection(True)
+        fn(*a)
+        t0 = time.perf_counter()
+        g = fn(*a)
+        ms = (time.perf_counter() - t0) * 1e3
+        sg = gc.last_stats()
+        gg = g[:, idx] if g.ndim == 2 else g[idx]
+        out["default_api"] = {"ms_per_call": ms, "value": n * m / (ms * 1e-3) / 1e9, "grid_path": sg["grid_path"],
+                              "n_devices": sg["n_devices"],
+                              "max_abs_diff_vs_general_over_sigma": float(np.max(np.abs(gg - one)) / np.std(one))}
+        gc.set_grid_detection(False)
+    return out
 
 
 def main():

@@ -181,7 +181,7 @@ struct Context {
     int64_t chunk_points = 0;
     int force_p = 0, force_l = 0;
     int poly_degree = 0;                 // 0: choose_degree's rule; else forced (gsf_set_poly_degree / GSF_POLY_DEGREE)
-    bool profiling = false;
+    int profiling = 0;                   // 0 off, 1 per call, 2 accumulate over calls (gsf_set_profiling)
     int grid_detect = -1;                // -1: env GSF_GRID_DETECT (default on), 0 off, 1 on
     gsf_stats last{};
     std::vector<int> last_devs;
@@ -560,7 +560,7 @@ int prepare_modes(DeviceCtx &d, const Problem &p, cudaStream_t st, double amp_fa
         a.z2 = d.d_raw + (size_t)(p.dim + 1) * N; a.z2s = 1;
         a.sf = p.kind == gsf::kFourier ? d.d_raw + (size_t)(p.dim + 2) * N : nullptr; a.sfs = 1;
     }
-    d.prep_timed = ctx().profiling;
+    d.prep_timed = ctx().profiling != 0;
     if (d.prep_timed) GSF_CUDA(cudaEventRecord(d.prep_beg, st));
     gsf::gsf_prep_modes<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(a);
     GSF_CUDA(cudaGetLastError());
@@ -574,7 +574,7 @@ void reset_call_counters(DeviceCtx &d)
     d.h2d_bytes = d.d2h_bytes = 0;
     d.launches = d.chunks = 0;
     d.staging_threads = 0;
-    d.prof_used = 0;
+    if (ctx().profiling != 2) d.prof_used = 0;
     d.prep_timed = false;
     d.status = GSF_OK;
     d.err.clear();
@@ -1243,12 +1243,13 @@ int run_host_call(Problem p, const GridSpec *grid)
     } else {
         std::vector<std::thread> th;
         std::vector<int> Ps(G), Ls(G);
+        const int threads_g = staging_threads(p.threads_hint, G);   // per device: issuing thread + its share of the crew
         for (int g = 0; g < G; ++g) {
             int64_t j0, j1;
             shard_bounds(p.M, G, g, &j0, &j1);
             th.emplace_back([&, g, j0, j1]() {
                 DeviceCtx &d = *used[g];
-                int r = run_shard(d, p, j0, j1, pos_kind, out_kind, &Ps[g], &Ls[g], 1);
+                int r = run_shard(d, p, j0, j1, pos_kind, out_kind, &Ps[g], &Ls[g], threads_g);
                 d.status = r;
                 if (r) d.err = g_err;   // g_err is thread-local to the worker
             });
@@ -1592,7 +1593,9 @@ int gsf_set_profiling(int enabled)
 {
     Context &c = ctx();
     std::lock_guard<std::mutex> lock(c.mu);
-    c.profiling = enabled != 0;
+    c.profiling = enabled < 0 ? 0 : (enabled > 2 ? 2 : enabled);
+    for (DeviceCtx *d : c.dctx)
+        if (d) d->prof_used = 0;
     return GSF_OK;
 }
 

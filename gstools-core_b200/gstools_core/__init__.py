@@ -623,6 +623,21 @@ def shard_bounds(n_points, n_shards, shard):
     return b.value, e.value
 
 
+def chunk_schedule(n_points, forced_chunk=0):
+    """Pipeline chunk sizes the library uses for n_points host-resident points (host logic only)."""
+    L = _load()
+    L.gsf_debug_chunk_schedule.argtypes = [_i64, _i64, ctypes.POINTER(_i64), _int]
+    L.gsf_debug_chunk_schedule.restype = _int
+    cap = 4096
+    buf = (_i64 * cap)()
+    n = L.gsf_debug_chunk_schedule(int(n_points), int(forced_chunk), buf, cap)
+    if n < 0:
+        cap = -n
+        buf = (_i64 * cap)()
+        n = L.gsf_debug_chunk_schedule(int(n_points), int(forced_chunk), buf, cap)
+    return list(buf[:n])
+
+
 def set_chunk_points(n):
     rc = _load().gsf_set_chunk_points(int(n))
     if rc:
@@ -679,7 +694,8 @@ class pinned:
 
 
 def set_profiling(enabled=True):
-    _load().gsf_set_profiling(1 if enabled else 0)
+    """False/0 off, True/1 per call, 2 accumulate kernel_ms over all calls until the next set_profiling."""
+    _load().gsf_set_profiling(int(enabled))
 
 
 def last_stats():

@@ -18,7 +18,8 @@ KIND = {"c1": "summate", "c2": "summate", "c3": "summate_incompr", "c4": "summat
 # FP64-pipe slots per point*mode: SURVEY.md 8(d4) "algorithmic" figure (libdevice-like sincos pair),
 # and what this implementation's single-cos formulation actually issues (gsf_kernels.cuh header).
 W_SURVEY = {"c1": 22, "c2": 23, "c3": 26, "c4": 22, "c5": 23}
-W_EXEC = {"c1": 14, "c2": 15, "c3": 17, "c4": 14, "c5": 15}
+# W_exec = dim + 5 + degree + nc; degree 6 (high) / 5 (throughput, chosen from 2^27 point*modes)
+W_EXEC = {"c1": 14, "c2": 14, "c3": 16, "c4": 13, "c5": 14}
 
 
 def _grid(shape, spacing, out=None):
@@ -32,6 +33,18 @@ def _grid(shape, spacing, out=None):
         idx = [None] * d
         idx[a] = slice(None)
         view[...] = ax[tuple(idx)]
+    return pos
+
+
+def _grid_range(shape, spacing, j0, j1):
+    """Columns [j0, j1) of `_grid(shape, spacing)` without building the rest (bit-identical values:
+    both evaluate float64(index) * spacing)."""
+    d = len(shape)
+    idx = np.arange(j0, j1, dtype=np.int64)
+    pos = np.empty((d, j1 - j0), dtype=np.float64)
+    for a in range(d - 1, -1, -1):
+        np.multiply(idx % shape[a], spacing[a], out=pos[a])
+        idx //= shape[a]
     return pos
 
 
@@ -52,10 +65,27 @@ def exponential_modes_3d(rng, n, len_scale):
     return g / np.abs(w) / len_scale
 
 
-def make(config, scale=1.0, pos_out=None):
+def make(config, scale=1.0, pos_out=None, point_range=None):
     """Return dict(kind=..., args=(...)) for gstools_core.<kind>(*args).
 
-    `scale` < 1 shrinks the number of points (grids keep their spacing, fewer cells per axis)."""
+    `scale` < 1 shrinks the number of points (grids keep their spacing, fewer cells per axis).
+    `point_range=(j0, j1)` builds only that contiguous shard of the positions (`m` stays the total;
+    `m_local` is the shard's size); pass a callable (m_total -> (j0, j1)) when the total is not
+    known to the caller."""
+    w = _make(config, scale, pos_out, point_range)
+    w.setdefault("m_local", w["args"][-1].shape[1])
+    w.setdefault("j0", 0)
+    return w
+
+
+def _shard(pr, m):
+    j0, j1 = pr(m) if callable(pr) else pr
+    if not (0 <= j0 <= j1 <= m):
+        raise ValueError("point_range %r outside [0, %d]" % ((j0, j1), m))
+    return int(j0), int(j1)
+
+
+def _make(config, scale, pos_out, point_range):
     c = config.lower()
     if c == "c1":
         rng = np.random.default_rng(1)
@@ -63,7 +93,11 @@ def make(config, scale=1.0, pos_out=None):
         k = gaussian_modes(rng, 2, n, 1.0)
         z1, z2 = rng.normal(size=n), rng.normal(size=n)
         pos = np.stack([np.linspace(0.0, 10.0, m), np.linspace(-5.0, 5.0, m)])
-        return dict(kind="summate", args=(k, z1, z2, pos), d=2, n=n, m=m, axes=None)
+        j0 = 0
+        if point_range is not None:
+            j0, j1 = _shard(point_range, m)
+            pos = np.ascontiguousarray(pos[:, j0:j1])
+        return dict(kind="summate", args=(k, z1, z2, pos), d=2, n=n, m=m, axes=None, j0=j0)
     if c in ("c2", "c5"):
         rng = np.random.default_rng(2 if c == "c2" else 5)
         n = 1000 if c == "c2" else 10_000
@@ -76,6 +110,11 @@ def make(config, scale=1.0, pos_out=None):
             f = scale ** (1 / 3)
             shape = (max(2, int(round(1000 * f))), max(2, int(round(1000 * f))), max(2, int(round(100 * f))))
             spacing = (0.1, 0.1, 0.1)
+        m = int(np.prod(shape))
+        if point_range is not None:
+            j0, j1 = _shard(point_range, m)
+            return dict(kind="summate", args=(k, z1, z2, _grid_range(shape, spacing, j0, j1)), d=3, n=n, m=m,
+                        axes=None, j0=j0)
         pos = _grid(shape, spacing, pos_out)
         return dict(kind="summate", args=(k, z1, z2, pos), d=3, n=n, m=pos.shape[1], axes=_axes(shape, spacing))
     if c == "c3":
@@ -84,6 +123,10 @@ def make(config, scale=1.0, pos_out=None):
         k = gaussian_modes(rng, 3, n, 10.0)
         z1, z2 = rng.normal(size=n), rng.normal(size=n)
         side = max(2, int(round(100 * scale ** (1 / 3))))
+        if point_range is not None:
+            j0, j1 = _shard(point_range, side ** 3)
+            return dict(kind="summate_incompr", args=(k, z1, z2, _grid_range((side,) * 3, (1.0,) * 3, j0, j1)), d=3,
+                        n=n, m=side ** 3, axes=None, j0=j0)
         pos = _grid((side, side, side), (1.0, 1.0, 1.0), pos_out)
         return dict(kind="summate_incompr", args=(k, z1, z2, pos), d=3, n=n, m=pos.shape[1],
                     axes=_axes((side, side, side), (1.0, 1.0, 1.0)))
@@ -99,6 +142,11 @@ def make(config, scale=1.0, pos_out=None):
         n = modes.shape[1]
         z1, z2 = rng.normal(size=n), rng.normal(size=n)
         side = max(2, int(round(4096 * scale ** 0.5)))
+        if point_range is not None:
+            j0, j1 = _shard(point_range, side * side)
+            return dict(kind="summate_fourier",
+                        args=(sf, modes, z1, z2, _grid_range((side, side), (period / side,) * 2, j0, j1)), d=2, n=n,
+                        m=side * side, axes=None, j0=j0)
         pos = _grid((side, side), (period / side, period / side), pos_out)
         return dict(kind="summate_fourier", args=(sf, modes, z1, z2, pos), d=2, n=n, m=pos.shape[1],
                     axes=_axes((side, side), (period / side, period / side)))
@@ -109,4 +157,4 @@ def subset_points(w, idx):
     """Same workload restricted to the point columns `idx` (for oracle checks of big configs)."""
     args = list(w["args"])
     args[-1] = np.ascontiguousarray(args[-1][:, idx])
-    return dict(w, args=tuple(args), m=len(idx), axes=None)
+    return dict(w, args=tuple(args), m=len(idx), m_local=len(idx), axes=None)

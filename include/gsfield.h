@@ -249,8 +249,10 @@ int gsf_set_variant(int points_per_thread, int lanes_per_point);
  * point*modes), or 5 / 6 to force one.  One degree per call; never changes with chunking or sharding.
  * Environment: GSF_POLY_DEGREE. */
 int gsf_set_poly_degree(int degree);
-/* Enable CUDA-event timing of the kernels (fills kernel_ms / prep_ms; adds event-sync overhead
- * only in gsf_get_last_stats). */
+/* CUDA-event timing of the summation kernels (fills kernel_ms / prep_ms; the event sync happens
+ * only in gsf_get_last_stats).  0 off; 1 per call; 2 accumulate: kernel_ms of gsf_get_last_stats is
+ * then the sum over every call since this setting was made (bench.py: kernel time and step time
+ * from one and the same loop). */
 int gsf_set_profiling(int enabled);
 int gsf_get_last_stats(gsf_stats *out);
 const char *gsf_last_error(void);

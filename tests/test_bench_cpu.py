@@ -26,7 +26,13 @@ def test_reference_arm_json_line():
     assert d["steps"] == 2 and d["warmup"] == 1 and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
-    assert "workload" in d["config"]
+    assert "workload" in d["config"] and d["scaling"] == "strong"
+    # the `ours` arm must print the very same config dict (the driver compares them)
+    import argparse
+    sys.path.insert(0, ROOT)
+    import bench
+    ns = argparse.Namespace(workload="c5", scale=0.002, gpus=1)
+    assert d["config"] == bench.config_for(ns, d["config"]["points_total"])
 
 
 def test_reference_arm_nonzero_rank_is_silent():
@@ -50,4 +56,4 @@ def test_workload_shapes_and_grids():
     assert w4["kind"] == "summate_fourier" and w4["n"] == 10_000 and len(w4["args"]) == 5
     w5 = workloads.make("c5", 1e-6)
     assert w5["n"] == 10_000 and w5["d"] == 3
-    assert workloads.W_EXEC["c2"] == 15 and workloads.W_SURVEY["c2"] == 23
+    assert workloads.W_EXEC["c2"] == 14 and workloads.W_SURVEY["c2"] == 23

@@ -30,7 +30,11 @@ def _reset():
     gc.set_variant(0, 0)
     gc.set_chunk_points(0)
     gc.set_devices(None)
+    gc.set_grid_detection(None)
+    gc.set_poly_degree(0)
     yield
+    gc.set_grid_detection(None)
+    gc.set_poly_degree(0)
 
 
 def rel_err(got, ref):
@@ -231,83 +235,153 @@ def test_large_phases():
 
 
 # ------------------------------------------------------------------------------- BASELINE configs
+@pytest.mark.parametrize("detect", [False, True])
 @pytest.mark.parametrize("cfg,scale", [("c1", 1.0), ("c2", 0.02), ("c3", 0.02), ("c4", 0.0005), ("c5", 0.00005)])
-def test_baseline_configs_scaled(cfg, scale):
+def test_baseline_configs_scaled(cfg, scale, detect):
     w = workloads.make(cfg, scale)
     ref = getattr(oracle, w["kind"])(*w["args"], oracle.max_threads())
+    gc.set_grid_detection(detect)
     got = getattr(gc, w["kind"])(*w["args"])
+    st = gc.last_stats()
     e = rel_err(got, ref)
-    print(cfg, "m=%d n=%d max|d|/sigma=%.3g" % (w["m"], w["n"], e))
+    print(cfg, "m=%d n=%d grid_path=%d deg=%d max|d|/sigma=%.3g" % (w["m"], w["n"], st["grid_path"], st["poly_degree"], e))
     assert e <= TOL
+    if not detect:
+        assert st["grid_path"] == 0
 
 
-def test_c2_full_size_subset_and_linearity():
-    """C2 at full size: oracle on a strided point subset + linearity in (z1, z2)."""
-    w = workloads.make("c2")
-    k, z1, z2, pos = w["args"]
+@pytest.mark.parametrize("deg", [5, 6])
+def test_both_polynomial_degrees_meet_the_contract(deg):
+    """The two shipped degrees of the cosine polynomial on every kind / dim, and the 1e-11 sigma
+    bar the throughput degree was chosen by (two orders inside the 1e-9 contract)."""
+    gc.set_poly_degree(deg)
+    for d, kind in ((2, "summate"), (3, "summate"), (2, "summate_incompr"), (3, "summate_incompr"), (3, "summate_fourier")):
+        k, z1, z2, pos = _rand(500 + d, d, 1000, 40_000, heavy=(d == 3))
+        args = (k, z1, z2, pos) if kind != "summate_fourier" else (np.abs(z1) + 0.1, k, z1, z2, pos)
+        ref = getattr(oracle, kind)(*args, oracle.max_threads())
+        got = getattr(gc, kind)(*args)
+        st = gc.last_stats()
+        assert st["poly_degree"] == deg and st["fp64_slots"] == d + 5 + deg + (d if kind == "summate_incompr" else 1)
+        e = rel_err(got, ref)
+        print("deg %d %s d=%d: max|d|/sigma=%.3g" % (deg, kind, d, e))
+        assert e <= 1e-11
+    # the degree is ONE decision per call: chunking must not change a bit
+    k, z1, z2, pos = _rand(9, 3, 300, 200_000, heavy=True)
+    one = gc.summate(k, z1, z2, pos)
+    gc.set_chunk_points(16 * 1024)
+    assert np.array_equal(one, gc.summate(k, z1, z2, pos))
+
+
+def test_degree_rule():
+    """Automatic rule: degree 6 below 2^27 point*modes (KATs to 1e-13), degree 5 from there on."""
+    k, z1, z2, pos = _rand(10, 3, 1000, 100_000)
+    gc.summate(k, z1, z2, pos)
+    assert gc.last_stats()["poly_degree"] == 6
+    k, z1, z2, pos = _rand(10, 3, 1000, 140_000)
+    gc.summate(k, z1, z2, pos)
+    assert gc.last_stats()["poly_degree"] == 5
+    gc.set_variant(1, 4)                                   # lanes split the modes: only built at degree 6
     got = gc.summate(k, z1, z2, pos)
-    idx = np.unique(np.concatenate([np.arange(0, w["m"], 499), np.arange(1024), np.arange(w["m"] - 1024, w["m"])]))
-    ref = oracle.summate(k, z1, z2, np.ascontiguousarray(pos[:, idx]), oracle.max_threads())
-    assert rel_err(got[idx], ref) <= TOL
+    assert gc.last_stats()["poly_degree"] == 6 and gc.last_stats()["lanes_per_point"] == 4
+    assert rel_err(got, oracle.summate(k, z1, z2, pos, oracle.max_threads())) <= TOL
+
+
+# ------------------------------------------------------------------------------- full-size configs
+# SURVEY.md section 8 c4: the oracle runs on >= 2^17 evenly strided points + the first / last 1024
+# points of every GPU shard and of every pipeline chunk.  Every test states (and asserts) which
+# device path produced the result: `grid_path` 0 = the general point x mode kernel (what bench.py
+# headlines), 1 = the auto-detected structured-grid GEMM.
+def _acceptance_idx(m, n_strided=1 << 17, edge=1024):
+    idx = [np.arange(0, m, max(1, m // n_strided)), np.arange(min(m, edge)), np.arange(max(0, m - edge), m)]
+    bounds = set()
+    run = 0
+    for c in gc.chunk_schedule(m):                     # the pipeline's own chunk boundaries
+        run += c
+        bounds.add(run)
+    for g in (2, 4, 8):                                # shard boundaries of 2 / 4 / 8 devices
+        for r in range(1, g):
+            bounds.add(gc.shard_bounds(m, g, r)[0])
+    for e in sorted(bounds):
+        if 0 < e < m:
+            idx.append(np.arange(max(0, e - edge), min(m, e + edge)))
+    return np.unique(np.concatenate(idx))
+
+
+def _full_size_check(cfg, detect, expect_grid_path):
+    w = workloads.make(cfg)
+    fn, ofn = getattr(gc, w["kind"]), getattr(oracle, w["kind"])
+    gc.set_grid_detection(detect)
+    try:
+        got = fn(*w["args"])
+        st = gc.last_stats()
+    finally:
+        gc.set_grid_detection(None)
+    assert st["grid_path"] == expect_grid_path, st
+    if expect_grid_path == 0:
+        assert st["poly_degree"] == 5                  # throughput-bound problems run the degree-5 kernels
+    idx = _acceptance_idx(w["m"])
+    assert idx.size >= (1 << 17)
+    ref = ofn(*workloads.subset_points(w, idx)["args"], oracle.max_threads())
+    sub = got[:, idx] if got.ndim == 2 else got[idx]
+    e = rel_err(sub, ref)
+    print("%s full size, grid_path=%d: %d oracle points, max|d|/sigma=%.3g, total_ms=%.2f chunks=%d deg=%d"
+          % (cfg, st["grid_path"], idx.size, e, st["total_ms"], st["n_chunks"], st["poly_degree"]))
+    assert e <= TOL
+    assert np.isfinite(got).all()
+    return w, got, idx, ref
+
+
+@pytest.mark.parametrize("detect,path", [(False, 0), (True, 1)])
+def test_c2_full_size(detect, path):
+    """C2 at full size on both device paths + linearity in (z1, z2)."""
+    w, got, idx, ref = _full_size_check("c2", detect, path)
+    k, z1, z2, pos = w["args"]
     # linearity: f(2*z1 + a, 2*z2 + b) = 2 f(z1, z2) + f(a, b)
-    rng = np.random.default_rng(0)
-    a, b = rng.normal(size=z1.size), rng.normal(size=z1.size)
-    lhs = gc.summate(k, 2 * z1 + a, 2 * z2 + b, pos)
-    rhs = 2 * got + gc.summate(k, a, b, pos)
+    gc.set_grid_detection(detect)
+    try:
+        rng = np.random.default_rng(0)
+        a, b = rng.normal(size=z1.size), rng.normal(size=z1.size)
+        lhs = gc.summate(k, 2 * z1 + a, 2 * z2 + b, pos)
+        rhs = 2 * got + gc.summate(k, a, b, pos)
+    finally:
+        gc.set_grid_detection(None)
     assert np.max(np.abs(lhs - rhs)) <= TOL * np.std(got)
+
+
+@pytest.mark.parametrize("detect,path", [(False, 0), (True, 1)])
+def test_c3_full_size(detect, path):
+    w, got, idx, ref = _full_size_check("c3", detect, path)
+    assert got.shape == (3, w["m"]) and got.flags.f_contiguous
+    # size-independent property: a repeated call is bit-identical
+    gc.set_grid_detection(detect)
+    try:
+        assert np.array_equal(got, gc.summate_incompr(*w["args"]))
+    finally:
+        gc.set_grid_detection(None)
+
+
+@pytest.mark.parametrize("detect,path", [(False, 0), (True, 1)])
+def test_c4_full_size(detect, path):
+    w, got, idx, ref = _full_size_check("c4", detect, path)
+    # periodicity of the Fourier method: the field repeats with period L = 100 along each axis
+    sf, modes, z1, z2, pos = w["args"]
+    sub = idx[:: max(1, idx.size // 8192)]
+    shifted = np.ascontiguousarray(pos[:, sub] + np.array([[100.0], [200.0]]))
+    again = gc.summate_fourier(sf, modes, z1, z2, shifted)
+    assert np.max(np.abs(again - got[sub])) <= 1e-9 * np.std(got)
+
+
+@pytest.mark.parametrize("detect,path", [(False, 0), (True, 1)])
+def test_c5_full_size(detect, path):
+    """C5 (1e4 modes x 1e8 points): the general kernel at 40 ring wraps per tile and ~100 pipeline
+    chunks -- the configuration bench.py headlines -- and the grid path the default API takes."""
+    w, got, idx, ref = _full_size_check("c5", detect, path)
+    assert w["m"] == 10 ** 8 and w["n"] == 10 ** 4
 
 
 def test_dfma_peak_runs():
     rate, ms = gc.dfma_peak(0, 20.0)
     assert rate > 1e12 and ms > 0
-
-
-# ------------------------------------------------------------------------------- full-size configs
-def _subset_idx(m, extra=()):
-    idx = [np.arange(0, m, max(1, m // 8192)), np.arange(min(m, 1024)), np.arange(max(0, m - 1024), m)]
-    for e in extra:                                    # chunk / shard boundaries
-        idx.append(np.arange(max(0, e - 64), min(m, e + 64)))
-    return np.unique(np.concatenate(idx))
-
-
-def test_c3_full_size_subset():
-    w = workloads.make("c3")
-    got = gc.summate_incompr(*w["args"])
-    chunk = 1024 * -(-(-(-w["m"] // 16)) // 1024)
-    idx = _subset_idx(w["m"], [chunk * i for i in range(1, 16)])
-    ref = oracle.summate_incompr(*workloads.subset_points(w, idx)["args"], oracle.max_threads())
-    assert got.shape == (3, w["m"]) and got.flags.f_contiguous
-    assert rel_err(got[:, idx], ref) <= TOL
-    # incompressibility is built into the projector: p(k).k = 0, so sum_a p_a k_a vanishes per mode;
-    # size-independent property of the output: repeated call is bit-identical
-    assert np.array_equal(got, gc.summate_incompr(*w["args"]))
-
-
-def test_c4_full_size_subset():
-    w = workloads.make("c4")
-    got = gc.summate_fourier(*w["args"])
-    idx = _subset_idx(w["m"], [1 << 20, 5 << 20])
-    ref = oracle.summate_fourier(*workloads.subset_points(w, idx)["args"], oracle.max_threads())
-    assert rel_err(got[idx], ref) <= TOL
-    # periodicity of the Fourier method: the field repeats with period L = 100 along each axis
-    sf, modes, z1, z2, pos = w["args"]
-    shifted = np.ascontiguousarray(pos[:, idx] + np.array([[100.0], [200.0]]))
-    again = gc.summate_fourier(sf, modes, z1, z2, shifted)
-    assert np.max(np.abs(again - got[idx])) <= 1e-9 * np.std(got)
-
-
-def test_c5_full_size_subset():
-    w = workloads.make("c5")
-    k, z1, z2, pos = w["args"]
-    assert w["m"] == 10 ** 8 and w["n"] == 10 ** 4
-    got = gc.summate(k, z1, z2, pos)
-    st = gc.last_stats()
-    idx = _subset_idx(w["m"], [(1 << 20) * i for i in (1, 2, 47, 94)])
-    ref = oracle.summate(k, z1, z2, np.ascontiguousarray(pos[:, idx]), oracle.max_threads())
-    e = rel_err(got[idx], ref)
-    print("c5 full: max|d|/sigma=%.3g total_ms=%.1f chunks=%d" % (e, st["total_ms"], st["n_chunks"]))
-    assert e <= TOL
-    assert np.isfinite(got).all()
 
 
 def test_multi_device_sharding_matches_single():
