@@ -191,14 +191,26 @@ int gso_summator_incompr(int d, int64_t N, int64_t M, const double *k, int64_t k
 #ifdef _OPENMP
     double *accs = (double *)calloc((size_t)nsplit * (size_t)M * d, sizeof(double));
     if (!accs) return GSO_ERR_ALLOC;
-#pragma omp parallel for schedule(static, 1) num_threads((int)nsplit)
+    /* The reference nests a second level of parallelism over the points inside every mode
+     * (`pos.par_iter().zip(&mut summed_modes)`, :142), so all threads stay busy even when N/100 is
+     * smaller than the pool.  Here: every mode range is also cut into point blocks, one task per
+     * (range, block); inside a task the loop nest stays mode-outer / point-inner like the
+     * reference's, and every point still receives its range's modes in index order -- the values
+     * do not depend on the blocking. */
+    int64_t pblocks = (num_threads + nsplit - 1) / nsplit;
+    if (pblocks > M / 1024) pblocks = M / 1024;
+    if (pblocks < 1) pblocks = 1;
+#pragma omp parallel for collapse(2) schedule(static, 1) num_threads(num_threads)
     for (int64_t s = 0; s < nsplit; ++s) {
-        int64_t i0 = N * s / nsplit, i1 = N * (s + 1) / nsplit;
-        double *acc = accs + (size_t)s * M * d;
-        double kv[3];
-        for (int64_t i = i0; i < i1; ++i) {
-            for (int a = 0; a < d; ++a) kv[a] = k[a * ks0 + i * ks1];
-            incompr_apply_mode(d, kv, z1[i * z1s], z2[i * z2s], M, pos, ps0, ps1, acc);
+        for (int64_t b = 0; b < pblocks; ++b) {
+            int64_t i0 = N * s / nsplit, i1 = N * (s + 1) / nsplit;
+            int64_t j0 = M * b / pblocks, j1 = M * (b + 1) / pblocks;
+            double *acc = accs + (size_t)s * M * d + (size_t)j0 * d;
+            double kv[3];
+            for (int64_t i = i0; i < i1; ++i) {
+                for (int a = 0; a < d; ++a) kv[a] = k[a * ks0 + i * ks1];
+                incompr_apply_mode(d, kv, z1[i * z1s], z2[i * z2s], j1 - j0, pos + j0 * ps1, ps0, ps1, acc);
+            }
         }
     }
     memcpy(out, accs, sizeof(double) * (size_t)M * d);
