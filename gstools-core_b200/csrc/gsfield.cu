@@ -56,6 +56,32 @@ int fail(int code, const char *fmt, ...)
     return code;
 }
 
+// GSF_TRACE=1: per-phase host timestamps of every call on stderr (latency work on small problems)
+struct Trace {
+    std::chrono::steady_clock::time_point t0, last;
+    static bool enabled()
+    {
+        static const bool e = []() { const char *v = getenv("GSF_TRACE"); return v && v[0] == '1'; }();
+        return e;
+    }
+    void begin()
+    {
+        if (!enabled()) return;
+        t0 = last = std::chrono::steady_clock::now();
+        fprintf(stderr, "[gsf-trace] ---- call\n");
+    }
+    void mark(const char *what)
+    {
+        if (!enabled()) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[gsf-trace] %-28s +%7.1f us  (%8.1f)\n", what,
+                std::chrono::duration<double, std::micro>(now - last).count(),
+                std::chrono::duration<double, std::micro>(now - t0).count());
+        last = now;
+    }
+};
+thread_local Trace g_trace;
+
 #define GSF_CUDA(call)                                                                     \
     do {                                                                                   \
         cudaError_t e_ = (call);                                                           \
@@ -654,6 +680,7 @@ int run_shard(DeviceCtx &d, const Problem &p, int64_t j_beg, int64_t j_end, int 
     cudaStream_t s0 = d.slot[0].stream;
     if (d.ws_used) GSF_CUDA(cudaStreamWaitEvent(s0, d.ev_ws, 0));
     if ((rc = prepare_modes(d, p, s0, gsf::amp_factor(p.deg)))) return rc;
+    g_trace.mark("shard: prepare modes");
 
     const bool pos_dev = pos_kind == 2, out_dev = out_kind == 2;
     // Chunk schedule.  Device-resident both ways => one launch.  Otherwise the first chunks are small
@@ -824,7 +851,9 @@ int run_shard(DeviceCtx &d, const Problem &p, int64_t j_beg, int64_t j_end, int 
             return c_done == n_chunks;
         }, n_chunks);
     }
+    g_trace.mark("shard: chunks issued");
     for (int s = 0; s < (n_chunks > 1 ? kSlots : 1); ++s) GSF_CUDA(cudaStreamSynchronize(d.slot[s].stream));
+    g_trace.mark("shard: streams synced");
     d.ws_used = false;   // everything that read the workspace has finished
     guard.armed = false;
     return GSF_OK;
@@ -1038,6 +1067,7 @@ int run_host_call(Problem p, const GridSpec *grid)
         return GSF_OK;
     }
     const auto t0 = std::chrono::steady_clock::now();
+    g_trace.begin();
 
     int pos_kind = 0, pos_dev = -1, out_kind, out_dev;
     if (!grid) classify(p.pos, &pos_kind, &pos_dev);
@@ -1115,6 +1145,7 @@ int run_host_call(Problem p, const GridSpec *grid)
     for (int g = 0; g < G; ++g)
         if ((rc = get_device_ctx(devs[g], &used[g]))) return rc;
 
+    g_trace.mark("classify + device ctx");
     // ---- structured grid?  explicit request, or exact auto-detection on host-resident positions
     GridSpec detected;
     const GridSpec *gs = grid;
@@ -1124,15 +1155,31 @@ int run_host_call(Problem p, const GridSpec *grid)
     // per-axis tables stay small next to HBM.
     // (the exact check is one long memory-bound pass: unlike the per-chunk staging copies it
     //  does profit from many threads)
-    const int detect_threads = std::max(threads1, std::min(8, (int)std::thread::hardware_concurrency() / 2));
+    const int detect_threads = std::max(threads1, std::min(8, (int)std::thread::hardware_concurrency() /
+                                                                   (2 * std::max(1, local_world_size()))));
+    // Speculation: the candidate structure (axis lengths from the first change of each coordinate)
+    // costs microseconds; the EXACT check of all points costs a pass over the whole array.  The
+    // grid kernels need only the candidate axes, so they start at once while pool workers verify;
+    // a mismatch cancels the grid path and the general kernel recomputes everything.
+    std::shared_ptr<GridVerify> verify;
     if (!gs && pos_kind != 2 && p.N >= 32 && (double)p.M * (double)p.N >= 2e7 && grid_detection_enabled() &&
-        detect_grid_host(p, &detected, p.threads_hint > 0 ? std::min(detect_threads, p.threads_hint) : detect_threads) &&
-        detected.rows() >= 16) {
+        grid_candidate_host(p, &detected) && detected.rows() >= 16) {
         const double table_bytes = 16.0 * (double)(p.N + 16) *
                                    ((double)detected.n[0] + (detected.dim == 3 ? (double)detected.n[1] : 0.0) +
                                     (double)detected.n_last() * p.nc());
-        if (table_bytes <= 8e9) gs = &detected;
+        if (table_bytes <= 8e9) {
+            gs = &detected;
+            verify = std::make_shared<GridVerify>(p, detected);
+            const int vt = p.threads_hint > 0 ? std::min(detect_threads, p.threads_hint) : detect_threads;
+            if (vt > 1) host_pool().submit(verify, vt - 1);
+            else if (!verify->finish()) { gs = nullptr; verify.reset(); }   // one thread: check first
+        }
     }
+    struct VerifyJoin {   // no exit path may leave workers reading the caller's positions
+        std::shared_ptr<GridVerify> *v;
+        ~VerifyJoin() { if (*v) (*v)->finish(); }
+    } verify_join{&verify};
+    const std::atomic<int> *cancel = verify ? &verify->bad : nullptr;
 
     // device-resident positions and result (synchronous API): detect on the device
     bool axes_on_device = false;
@@ -1155,7 +1202,7 @@ int run_host_call(Problem p, const GridSpec *grid)
     if (gs) {
         const int64_t R = gs->rows();
         if (G == 1) {
-            rc = run_grid(*used[0], p, *gs, 0, R, out_kind, threads1, axes_on_device);
+            rc = run_grid(*used[0], p, *gs, 0, R, out_kind, threads1, axes_on_device, cancel);
         } else {
             std::vector<std::thread> th;
             for (int g = 0; g < G; ++g) {
@@ -1163,7 +1210,7 @@ int run_host_call(Problem p, const GridSpec *grid)
                 const int64_t r1 = g + 1 == G ? R : R * (g + 1) / G / 32 * 32;
                 th.emplace_back([&, g, r0, r1]() {
                     DeviceCtx &d = *used[g];
-                    int r = run_grid(d, p, *gs, r0, r1, out_kind, 1);
+                    int r = run_grid(d, p, *gs, r0, r1, out_kind, 1, false, cancel);
                     d.status = r;
                     if (r) d.err = g_err;
                 });
@@ -1175,6 +1222,18 @@ int run_host_call(Problem p, const GridSpec *grid)
                     g_err = used[g]->err;
                 }
         }
+        if (verify) {
+            const bool is_grid = verify->finish();
+            verify.reset();
+            g_trace.mark("grid: verification joined");
+            if (!is_grid) {   // speculation failed: not a grid after all
+                if (rc) return rc;
+                gs = nullptr;
+            }
+        }
+    }
+    if (gs) {
+        // structured-grid path done
     } else if (G == 1) {
         // Zero-copy: pinned host positions and result are mapped into the device address space
         // (UVA), so ONE full-size launch can read/write them over PCIe directly -- no chunking, no
@@ -1221,6 +1280,7 @@ int run_host_call(Problem p, const GridSpec *grid)
                 if (cudaHostGetDevicePointer(&dpos, sl.h_pos, 0) == cudaSuccess &&
                     cudaHostGetDevicePointer(&dout, sl.h_out, 0) == cudaSuccess) {
                     gather_pos(p, 0, p.M, sl.h_pos, 1);
+                    g_trace.mark("small: gather pos");
                     Problem q = p;
                     q.pos = static_cast<const double *>(dpos); q.ps0 = p.M; q.ps1 = 1;
                     q.out = static_cast<double *>(dout);
@@ -1230,6 +1290,7 @@ int run_host_call(Problem p, const GridSpec *grid)
                     q.zero_copy = true;
                     rc = run_shard(d0, q, 0, p.M, 2, 2, &P, &L, threads1);
                     if (!rc) scatter_out(p, lay, 0, p.M, sl.h_out, 1);
+                    g_trace.mark("small: scatter out");
                     d0.h2d_bytes += (int64_t)p.dim * p.M * 8;
                     d0.d2h_bytes += (int64_t)nc * p.M * 8;
                     zc = true;
@@ -1266,6 +1327,7 @@ int run_host_call(Problem p, const GridSpec *grid)
     if (rc) return rc;
     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     collect_stats(p, used, ms, P, L, pos_kind, out_kind, gs ? (grid ? 2 : 1) : 0);
+    g_trace.mark("done");
     return GSF_OK;
 }
 

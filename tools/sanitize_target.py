@@ -23,4 +23,27 @@ k2, a, b = modes(2, 100)
 gc.summate_grid(k2, a, b, axes2); gc.summate_fourier_grid(a, k2, a, b, axes2)
 mat = rng.normal(size=(70, 70)); vecs = rng.normal(size=(70, 333)); cond = rng.normal(size=70)
 gc.calc_field_krige_and_variance(mat, vecs, cond); gc.calc_field_krige(mat, vecs, cond)
+# degree-5 kernels (forced: the automatic rule picks them only for large problems) and the staged pageable pipeline
+gc.set_poly_degree(5)
+gc.summate(k, z1, z2, rng.uniform(0, 9, size=(3, 70000))); gc.summate_incompr(k, z1, z2, rng.uniform(0, 9, size=(3, 70000)))
+gc.set_chunk_points(8192); gc.summate(k, z1, z2, rng.uniform(0, 9, size=(3, 70000))); gc.set_chunk_points(0)
+gc.set_poly_degree(0)
+# detected grid (speculative start + exact verification) and a near-grid that fails verification
+g = np.stack([x.ravel() for x in np.meshgrid(*axes3, indexing="ij")]); kk, a3, b3 = modes(3, 4000)
+gc.set_grid_detection(True); gc.summate(kk, a3, b3, g); g[1, 777] += 1e-9; gc.summate(kk, a3, b3, g); gc.set_grid_detection(None)
+# variogram estimators (src/variogram.rs): structured / masked, unstructured (Euclid, Haversine), directional
+f2 = rng.normal(size=(60, 45)); mask = rng.uniform(size=(60, 45)) < 0.2
+for est in ("m", "c"):
+    gc.variogram_structured(f2, est); gc.variogram_ma_structured(f2, mask, est)
+for d in (1, 2, 3, 5):
+    pts = rng.uniform(0, 10, size=(d, 700)); fld = rng.normal(size=(2, 700)); edges = np.linspace(0, 6, 13)
+    for est in ("m", "c"):
+        gc.variogram_unstructured(fld, edges, pts, est, "e")
+    gc.variogram_unstructured(fld, np.array([0.0, 2.0, 1.0, 3.0, 2.5]), pts, "m", "e")     # non-monotone edges: generic kernel
+    if d in (2, 3):
+        dirs = rng.normal(size=(3, d)); dirs /= np.linalg.norm(dirs, axis=1)[:, None]
+        gc.variogram_directional(fld, edges, pts, dirs, np.pi / 6, 1.5, False, "m")
+        gc.variogram_directional(fld, edges, pts, dirs, np.pi / 6, -1.0, True, "c")
+ll = np.stack([rng.uniform(-80, 80, size=500), rng.uniform(-170, 170, size=500)])
+gc.variogram_unstructured(rng.normal(size=(1, 500)), np.linspace(0, 2, 9), ll, "m", "h")
 print("sanitize target done")
