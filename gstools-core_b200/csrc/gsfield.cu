@@ -639,13 +639,26 @@ std::vector<int64_t> chunk_schedule(int64_t m, bool single_launch, int64_t force
         const int64_t chunk = std::min((forced_chunk + 1023) / 1024 * 1024, m);
         for (int64_t done = 0; done < m; done += chunk) sizes.push_back(std::min(chunk, m - done));
     } else {
-        const int64_t lo = 1 << 15;
-        int64_t cap = std::min<int64_t>(1 << 20, std::max<int64_t>(1 << 16, m / 6));
+        // knobs (tools/chunk_schedule_probe.py): first chunk, growth factor of the ramps, cap as a
+        // fraction of the shard and in absolute points, number of down-ramp chunks
+        static const struct Knobs {
+            int64_t lo, cap_abs; int growth, cap_div, down_max;
+            static int64_t env(const char *n, int64_t dflt) { const char *e = getenv(n); return e && *e ? atoll(e) : dflt; }
+            Knobs() : lo(env("GSF_CHUNK_FIRST", 1 << 15)), cap_abs(env("GSF_CHUNK_CAP", 1 << 20)),
+                      growth((int)env("GSF_CHUNK_GROWTH", 2)), cap_div((int)env("GSF_CHUNK_CAP_DIV", 6)),
+                      down_max((int)env("GSF_CHUNK_DOWN", 64)) {}
+        } kn;
+        const int64_t lo = std::max<int64_t>(1024, kn.lo / 1024 * 1024);
+        const int growth = std::max(2, kn.growth);
+        int64_t cap = std::min<int64_t>(kn.cap_abs, std::max<int64_t>(1 << 16, m / std::max(1, kn.cap_div)));
         cap = cap / 1024 * 1024;
         std::vector<int64_t> up, down;
         int64_t used = 0;
-        for (int64_t c = lo; c < cap && used + c + c / 2 <= m / 2; c *= 2) { up.push_back(c); used += c; }
-        for (int64_t c = lo; c < cap && used + c + c / 2 <= m * 3 / 4; c *= 2) { down.push_back(c); used += c; }
+        for (int64_t c = lo; c < cap && used + c + c / 2 <= m / 2; c *= growth) { up.push_back(c); used += c; }
+        for (int64_t c = lo; c < cap && used + c + c / 2 <= m * 3 / 4 && (int)down.size() < kn.down_max; c *= growth) {
+            down.push_back(c);
+            used += c;
+        }
         int64_t rest = m - used;
         sizes = up;
         while (rest > 0) {
@@ -939,7 +952,7 @@ class PinnedPool {
     static size_t cap()
     {
         const char *e = getenv("GSF_PINNED_CACHE_MB");
-        return (size_t)(e && *e ? atoll(e) : 1024) << 20;
+        return (size_t)(e && *e ? atoll(e) : 2048) << 20;
     }
     // live (handed-out) pinned bytes: GSF_PINNED_LIVE_MB, default min(4 GiB, physical RAM / 8)
     static size_t live_cap()
@@ -1279,7 +1292,7 @@ int run_host_call(Problem p, const GridSpec *grid)
                 void *dpos = nullptr, *dout = nullptr;
                 if (cudaHostGetDevicePointer(&dpos, sl.h_pos, 0) == cudaSuccess &&
                     cudaHostGetDevicePointer(&dout, sl.h_out, 0) == cudaSuccess) {
-                    gather_pos(p, 0, p.M, sl.h_pos, 1);
+                    gather_pos_part(p, 0, p.M, 0, p.M, sl.h_pos, true);
                     g_trace.mark("small: gather pos");
                     Problem q = p;
                     q.pos = static_cast<const double *>(dpos); q.ps0 = p.M; q.ps1 = 1;
@@ -1289,7 +1302,7 @@ int run_host_call(Problem p, const GridSpec *grid)
                     else { q.os0 = p.M; q.os1 = 1; }
                     q.zero_copy = true;
                     rc = run_shard(d0, q, 0, p.M, 2, 2, &P, &L, threads1);
-                    if (!rc) scatter_out(p, lay, 0, p.M, sl.h_out, 1);
+                    if (!rc) scatter_out_part(p, lay, 0, p.M, 0, p.M, sl.h_out, true);
                     g_trace.mark("small: scatter out");
                     d0.h2d_bytes += (int64_t)p.dim * p.M * 8;
                     d0.d2h_bytes += (int64_t)nc * p.M * 8;

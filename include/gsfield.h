@@ -225,7 +225,8 @@ int gsf_set_devices(const int *device_ids, int n);
  * buffer needs no staging copy.  gsf_host_free returns the block to the pool.  Page-locked memory
  * cannot be swapped, so the pool refuses (GSF_ERR_ALLOC) once the blocks handed out exceed
  * GSF_PINNED_LIVE_MB (default min(4 GiB, RAM/8)); freed blocks are cached up to GSF_PINNED_CACHE_MB
- * (default 1024). */
+ * (default 2048: two results of the largest size the Python module pins, so that the usual
+ * `field = summate(...)` rebinding in a loop never reaches cudaMallocHost). */
 int gsf_host_alloc(int64_t bytes, void **ptr);
 int gsf_host_free(void *ptr);
 /* Page-lock / unlock a caller-owned host range (cudaHostRegister): positions that are evaluated

@@ -9,6 +9,8 @@ KEYS = ['gpu__time_duration.sum', 'sm__cycles_elapsed.max.per_second', 'launch__
         'sm__warps_active.avg.per_cycle_active', 'sm__cycles_active.avg',
         'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active', 'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed',
         'smsp__issue_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum',
+        'sm__inst_executed_pipe_fp64.sum', 'smsp__sass_thread_inst_executed_op_dfma_pred_on.sum',
+        'smsp__sass_thread_inst_executed_op_dadd_pred_on.sum', 'smsp__sass_thread_inst_executed_op_dmul_pred_on.sum',
         'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed',
         'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum',
         'dram__bytes_read.sum', 'dram__bytes_write.sum', 'lts__t_bytes.sum', 'lts__t_sectors_op_read.sum',
