@@ -225,7 +225,7 @@ def run_reference(args):
         "e2e": {"value": gpm, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -451,7 +451,7 @@ def run_ours(args):
     if world == 1 and not args.no_cpu_baseline:
         _, info, _ = cpu_reference_rate(args.workload, args.scale, args.cpu_seconds)
         line["cpu_baseline"] = info
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -629,6 +629,25 @@ def in_process_block(gc, workloads, args, world):
     return out
 
 
+def claim_stdout():
+    """Keep stdout to the ONE JSON line: libraries (NCCL prints its version banner on stdout) write
+    to fd 1 behind Python's back, so fd 1 is pointed at stderr for the run and the line goes to a
+    private duplicate of the original stdout."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+_JSON_OUT = None
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     args = parse()
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
@@ -641,6 +660,7 @@ def main():
         os.execv(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
                                   "--nproc-per-node", str(args.gpus), "--master-addr", "127.0.0.1",
                                   "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:])
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -128,42 +128,47 @@ __device__ __forceinline__ double div_pi(double x)
     return fma(x, inv_pi_hi, __dmul_rn(x, inv_pi_lo));
 }
 
-__global__ void gsf_prep_modes(PrepArgs a)
+// One mode -> one record.  `k_of(d)`, `z1`, `z2`, `sf` are the caller's raw values of this mode;
+// shared by gsf_prep_modes (records in global memory) and gsf_small_kernel (records built per CTA in
+// shared memory), so both produce bit-identical records.
+template <class KOf>
+__device__ __forceinline__ void prep_record(int D, bool incompr, double scale, double z1, double z2, bool has_sf,
+                                            double sf, KOf k_of, double *rec)
 {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n_modes) return;
-    const int D = a.dim;
-    const int NC = a.incompr ? D : 1;
+    const int NC = incompr ? D : 1;
     const int R = rec_doubles(D, NC);
-    double *rec = a.rec + i * R;
-
-    const double z1 = a.z1[i * a.z1s];
-    const double z2 = a.z2[i * a.z2s];
     double amp = hypot(z1, z2);
     const double th = div_pi(atan2(z2, z1));
-    if (a.sf) amp = __dmul_rn(a.sf[i * a.sfs], amp);   // src/field.rs:243
-    if (a.scale != 1.0) amp = __dmul_rn(amp, a.scale);
+    if (has_sf) amp = __dmul_rn(sf, amp);              // src/field.rs:243
+    if (scale != 1.0) amp = __dmul_rn(amp, scale);
 
     double kk = 0.0;
     for (int d = 0; d < D; ++d) {
-        const double kd = a.k[d * a.ks0 + i * a.ks1];
+        const double kd = k_of(d);
         rec[d] = div_pi(kd);
         kk = __dadd_rn(kk, __dmul_rn(kd, kd));          // ShortVec::dot, src/short_vec.rs:31-33
     }
     rec[D] = -th;                                       // the dot-product chain starts from -theta
-    if (!a.incompr) {
+    if (!incompr) {
         rec[D + 1] = amp;
     } else {
         // projector, src/field.rs:138,148,151:  k_2 = k0/|k|^2 ; p0 = 1 - k0*k_2 ; pa = -(ka*k_2)
-        const double k0 = a.k[i * a.ks1];
+        const double k0 = k_of(0);
         const double k_2 = __ddiv_rn(k0, kk);           // NaN for k = 0, as in the reference
         rec[D + 1] = __dmul_rn(__dadd_rn(1.0, -__dmul_rn(k0, k_2)), amp);
-        for (int d = 1; d < D; ++d) {
-            const double kd = a.k[d * a.ks0 + i * a.ks1];
-            rec[D + 1 + d] = __dmul_rn(-__dmul_rn(kd, k_2), amp);
-        }
+        for (int d = 1; d < D; ++d) rec[D + 1 + d] = __dmul_rn(-__dmul_rn(k_of(d), k_2), amp);
     }
     for (int d = D + 1 + NC; d < R; ++d) rec[d] = 0.0;
+}
+
+__global__ void gsf_prep_modes(PrepArgs a)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n_modes) return;
+    const int NC = a.incompr ? a.dim : 1;
+    prep_record(a.dim, a.incompr != 0, a.scale, a.z1[i * a.z1s], a.z2[i * a.z2s], a.sf != nullptr,
+                a.sf ? a.sf[i * a.sfs] : 1.0, [&](int d) { return a.k[d * a.ks0 + i * a.ks1]; },
+                a.rec + i * rec_doubles(a.dim, NC));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -458,6 +463,67 @@ __global__ void __launch_bounds__(kThreads) gsf_sum_kernel_anyd(SumArgs a)
         acc = fma(__ldg(m + D + 1), cospi_signed<DEG>(t, coef), acc);
     }
     a.out[j * a.os1] = acc;
+}
+
+// ------------------------------------------------------------------------------------------
+// One-launch path for small problems (C1: 100 modes x 1e4 points, where a call is launch latency,
+// not arithmetic).  The RAW modes travel inside the kernel parameters (rows k[0..D-1], z1, z2, sf of
+// n_modes doubles each -- no upload, no pre-pass launch); every CTA builds the <= kModeBlock records
+// in shared memory with prep_record and then runs the same recipe as gsf_sum_kernel<D,NC,1,L,kHiDeg>
+// (one point per thread, `lanes` lanes per point, same mode order and butterfly => bit-identical
+// results).  CAP = doubles of raw modes that fit: 480 keeps the launch inside the classic 4 KB
+// parameter block, 1536 uses the large-parameter launch (CUDA 12.1+).
+template <int CAP>
+struct SmallArgs {
+    SumArgs a;            // rec unused
+    double scale;
+    int lanes;            // L: power of two <= 32
+    int has_sf;
+    double raw[CAP];
+};
+
+template <int D, int NC, int CAP>
+__global__ void __launch_bounds__(kThreads) gsf_small_kernel(const __grid_constant__ SmallArgs<CAP> s)
+{
+    constexpr int R = rec_doubles(D, NC);
+    __shared__ __align__(16) double s_rec[kModeBlock * R];
+    const int tid = threadIdx.x;
+    const int N = (int)s.a.n_modes;
+    for (int i = tid; i < N; i += kThreads)
+        prep_record(D, NC > 1, s.scale, s.raw[D * N + i], s.raw[(D + 1) * N + i], s.has_sf != 0,
+                    s.has_sf ? s.raw[(D + 2) * N + i] : 1.0, [&](int d) { return s.raw[d * N + i]; }, s_rec + i * R);
+    const int L = s.lanes;
+    const int sub = tid & (L - 1);
+    const int grp = tid / L;
+    const int64_t j = (int64_t)blockIdx.x * (kThreads / L) + grp;
+    const int64_t jc = j < s.a.n_points ? j : s.a.n_points - 1;
+    double x[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) x[d] = __ldg(s.a.pos + d * s.a.ps0 + jc * s.a.ps1);
+    double acc[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) acc[c] = sub == 0 ? s.a.offset[c < 3 ? c : 0] : 0.0;
+    const PolyCoef coef = {{s.a.coef[0], s.a.coef[1], s.a.coef[2], s.a.coef[3], s.a.coef[4], s.a.coef[5], s.a.coef[6]}};
+    __syncthreads();
+    for (int i = sub; i < N; i += L) {
+        const double *m = s_rec + i * R;
+        double t = m[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) t = fma(m[d], x[d], t);
+        const double y = cospi_signed<kHiDeg>(t, coef);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) acc[c] = fma(m[D + 1 + c], y, acc[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        double v = acc[c];
+        for (int o = L >> 1; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        acc[c] = v;
+    }
+    if (sub == 0 && j < s.a.n_points) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) s.a.out[c * s.a.os0 + j * s.a.os1] = acc[c];
+    }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -379,6 +379,8 @@ struct Problem {
     int deg = gsf::kHiDeg;               // degree of the cosine polynomial, ONE per call (choose_degree)
     double scale = 1.0;                  // out = scale * sum + offset[a]   
     double offset[3] = {0.0, 0.0, 0.0};
+    // memory kind of the mode arrays (classify): filled once per call by run_host_call, -1 = not yet known
+    int mem_k = -1, mem_k_dev = -1, mem_z1 = -1, mem_z2 = -1, mem_sf = -1;
     int nc() const { return kind == gsf::kIncompr ? dim : 1; }
     int rec() const { return gsf::rec_doubles(dim, nc()); }
 };
@@ -537,12 +539,15 @@ int prepare_modes(DeviceCtx &d, const Problem &p, cudaStream_t st, double amp_fa
         if (d.rec_cap != cap_before) d.rec_valid = false;
     }
     if (N == 0) return GSF_OK;
-    int kk, kd, tmp;
-    classify(p.k, &kk, &kd);
-    int k1, k2, k3 = kk;
-    classify(p.z1, &k1, &tmp);
-    classify(p.z2, &k2, &tmp);
-    if (p.kind == gsf::kFourier) classify(p.sf, &k3, &tmp);
+    int kk = p.mem_k, kd = p.mem_k_dev, tmp;
+    if (kk < 0) classify(p.k, &kk, &kd);
+    int k1 = p.mem_z1, k2 = p.mem_z2, k3 = kk;
+    if (k1 < 0) classify(p.z1, &k1, &tmp);
+    if (k2 < 0) classify(p.z2, &k2, &tmp);
+    if (p.kind == gsf::kFourier) {
+        k3 = p.mem_sf;
+        if (k3 < 0) classify(p.sf, &k3, &tmp);
+    }
     const bool all_dev = kk == 2 && k1 == 2 && k2 == 2 && k3 == 2;
     const bool all_host = kk != 2 && k1 != 2 && k2 != 2 && k3 != 2;
     if (!all_dev && !all_host)
@@ -627,6 +632,117 @@ struct DrainOnError {
 };
 
 #include "gsf_host_staging.inc"
+
+// ---------------------------------------------------------------------------------------------
+// One-launch path for small host-resident problems (gsf_small_kernel): raw modes inside the kernel
+// parameters, positions gathered into a pinned buffer the kernel reads in place, result written to a
+// pinned buffer and scattered on return.  One launch, one stream sync, no copy-engine work.
+constexpr int kSmallCapA = 480, kSmallCapB = 1536;
+
+template <int CAP>
+int launch_small(DeviceCtx &d, const Problem &p, const double *hpos, double *hout, int64_t os0, int64_t os1, int L,
+                 cudaStream_t st)
+{
+    typedef void (*Fn)(const gsf::SmallArgs<CAP>);
+    Fn fn = nullptr;
+    const bool inc = p.kind == gsf::kIncompr;
+    if (!inc && p.dim == 1) fn = gsf::gsf_small_kernel<1, 1, CAP>;
+    else if (!inc && p.dim == 2) fn = gsf::gsf_small_kernel<2, 1, CAP>;
+    else if (!inc && p.dim == 3) fn = gsf::gsf_small_kernel<3, 1, CAP>;
+    else if (inc && p.dim == 2) fn = gsf::gsf_small_kernel<2, 2, CAP>;
+    else if (inc && p.dim == 3) fn = gsf::gsf_small_kernel<3, 3, CAP>;
+    if (!fn) return fail(GSF_ERR_ARG, "no small-problem kernel for dim=%d", p.dim);
+    static thread_local gsf::SmallArgs<CAP> s;   // 4 / 12 KB: kept off the stack, rebuilt every call
+    const int64_t N = p.N;
+    s.a = SumArgs{};
+    s.a.dim = p.dim;
+    s.a.n_modes = N;
+    s.a.pos = hpos; s.a.ps0 = p.M; s.a.ps1 = 1;
+    s.a.n_points = p.M;
+    s.a.out = hout; s.a.os0 = os0; s.a.os1 = os1;
+    for (int c = 0; c < 3; ++c) s.a.offset[c] = p.offset[c];
+    gsf::poly_constants(gsf::kHiDeg, s.a.coef);
+    s.scale = p.scale * gsf::amp_factor(gsf::kHiDeg);
+    s.lanes = L;
+    s.has_sf = p.kind == gsf::kFourier;
+    double *r = s.raw;
+    for (int a = 0; a < p.dim; ++a)
+        for (int64_t i = 0; i < N; ++i) *r++ = p.k[a * p.ks0 + i * p.ks1];
+    for (int64_t i = 0; i < N; ++i) *r++ = p.z1[i * p.z1s];
+    for (int64_t i = 0; i < N; ++i) *r++ = p.z2[i * p.z2s];
+    if (s.has_sf)
+        for (int64_t i = 0; i < N; ++i) *r++ = p.sf[i * p.sfs];
+    const int64_t per_cta = kThreads / L;
+    const int64_t grid = (p.M + per_cta - 1) / per_cta;
+    cudaEvent_t e1 = nullptr;
+    if (ctx().profiling) {
+        if (d.prof_used == d.prof.size()) {
+            cudaEvent_t a0, a1;
+            GSF_CUDA(cudaEventCreate(&a0));
+            GSF_CUDA(cudaEventCreate(&a1));
+            d.prof.emplace_back(a0, a1);
+        }
+        GSF_CUDA(cudaEventRecord(d.prof[d.prof_used].first, st));
+        e1 = d.prof[d.prof_used].second;
+        d.prof_used++;
+    }
+    fn<<<(unsigned)grid, kThreads, 0, st>>>(s);
+    GSF_CUDA(cudaGetLastError());
+    if (e1) GSF_CUDA(cudaEventRecord(e1, st));
+    d.launches++;
+    d.h2d_bytes += (int64_t)((r - s.raw) * sizeof(double));
+    return GSF_OK;
+}
+
+// raw-mode doubles the fused kernel needs for problem p; 0 if p does not qualify
+int64_t small_fused_rows(const Problem &p)
+{
+    static const bool enabled = []() { const char *e = getenv("GSF_SMALL_FUSED"); return !(e && e[0] == '0'); }();
+    const Context &c = ctx();
+    if (!enabled || p.N < 1 || p.N > gsf::kModeBlock || p.dim > 3 || p.deg != gsf::kHiDeg) return 0;
+    if (c.force_p > 0 || c.force_l > 0) return 0;                 // a forced (P, L) variant means the general kernels
+    if (p.mem_k != 0 && p.mem_k != 1) return 0;                   // host-resident modes only
+    if ((p.mem_z1 != 0 && p.mem_z1 != 1) || (p.mem_z2 != 0 && p.mem_z2 != 1)) return 0;
+    if (p.kind == gsf::kFourier && p.mem_sf != 0 && p.mem_sf != 1) return 0;
+    const int64_t rows = (p.dim + 2 + (p.kind == gsf::kFourier ? 1 : 0)) * p.N;
+    return rows <= kSmallCapB ? rows : 0;
+}
+
+int run_small_fused(DeviceCtx &d, const Problem &p, int64_t rows, int *L_used)
+{
+    GSF_CUDA(cudaSetDevice(d.dev));
+    reset_call_counters(d);
+    Slot &sl = d.slot[0];
+    const int nc = p.nc();
+    int rc;
+    if ((rc = ensure_cap(&sl.h_pos, &sl.h_pos_cap, (size_t)p.dim * p.M, true))) return rc;
+    if ((rc = ensure_cap(&sl.h_out, &sl.h_out_cap, (size_t)nc * p.M, true))) return rc;
+    OutLayout lay;
+    lay.aos = nc > 1 && p.os0 == 1 && p.os1 == nc;
+    lay.direct = false;
+    gather_pos_part(p, 0, p.M, 0, p.M, sl.h_pos, true);
+    g_trace.mark("small: gather pos");
+    // lanes per point: as choose_variant -- widen until every SM has two CTAs, >= 32 modes per lane
+    int L = 1;
+    const int64_t ctas1 = (p.M + kThreads - 1) / kThreads;
+    while (L < 32 && ctas1 * L < 2 * d.sm_count && p.N >= 32 * L) L *= 2;
+    *L_used = L;
+    // (cudaMallocHost memory: under UVA the device address equals the host address)
+    const int64_t os0 = nc == 1 ? 0 : (lay.aos ? 1 : p.M), os1 = nc > 1 && lay.aos ? nc : 1;
+    rc = rows <= kSmallCapA ? launch_small<kSmallCapA>(d, p, sl.h_pos, sl.h_out, os0, os1, L, sl.stream)
+                            : launch_small<kSmallCapB>(d, p, sl.h_pos, sl.h_out, os0, os1, L, sl.stream);
+    g_trace.mark("small: launched");
+    const cudaError_t e = cudaStreamSynchronize(sl.stream);   // also on a failed launch: nothing may stay in flight
+    if (rc) return rc;
+    GSF_CUDA(e);
+    g_trace.mark("small: synced");
+    scatter_out_part(p, lay, 0, p.M, 0, p.M, sl.h_out, true);
+    g_trace.mark("small: scatter out");
+    d.h2d_bytes += (int64_t)p.dim * p.M * 8;
+    d.d2h_bytes += (int64_t)nc * p.M * 8;
+    d.chunks = 1;
+    return GSF_OK;
+}
 
 // Chunk sizes for streaming m points through the pipeline slots (see run_shard).
 std::vector<int64_t> chunk_schedule(int64_t m, bool single_launch, int64_t forced_chunk)
@@ -1104,11 +1220,8 @@ int run_host_call(Problem p, const GridSpec *grid)
     // stream-ordered gsf_summate_on_stream takes the caller's stream instead and never syncs.)
     {
         int seen[8], n_seen = 0;
-        auto sync_owner = [&](const void *ptr) {
-            int k = 0, dv = -1;
-            if (!ptr) return;
-            classify(ptr, &k, &dv);
-            if (k != 2 || dv < 0) return;
+        auto sync_owner = [&](int dv) {
+            if (dv < 0) return;
             for (int i = 0; i < n_seen; ++i)
                 if (seen[i] == dv) return;
             if (n_seen < 8) seen[n_seen++] = dv;
@@ -1118,13 +1231,20 @@ int run_host_call(Problem p, const GridSpec *grid)
             cudaSetDevice(prev);
             cudaGetLastError();
         };
-        if (pos_kind == 2) sync_owner(p.pos);
-        if (out_kind == 2) sync_owner(p.out);
-        if (p.N > 0) {
-            sync_owner(p.k);
-            sync_owner(p.z1);
-            sync_owner(p.z2);
-            if (p.kind == gsf::kFourier) sync_owner(p.sf);
+        if (pos_kind == 2) sync_owner(pos_dev);
+        if (out_kind == 2) sync_owner(out_dev);
+        if (p.N > 0) {   // every mode array is classified here, once per call (prepare_modes reuses it)
+            int dv = -1;
+            classify(p.k, &p.mem_k, &p.mem_k_dev);
+            if (p.mem_k == 2) sync_owner(p.mem_k_dev);
+            classify(p.z1, &p.mem_z1, &dv);
+            if (p.mem_z1 == 2) sync_owner(dv);
+            classify(p.z2, &p.mem_z2, &dv);
+            if (p.mem_z2 == 2) sync_owner(dv);
+            if (p.kind == gsf::kFourier) {
+                classify(p.sf, &p.mem_sf, &dv);
+                if (p.mem_sf == 2) sync_owner(dv);
+            }
         }
     }
     if (pos_kind == 2 || out_kind == 2) {
@@ -1279,7 +1399,14 @@ int run_host_call(Problem p, const GridSpec *grid)
         // ring on the host and let the kernel read / write the pinned buffers in place -- saves the
         // explicit H2D and D2H copies and their launch latencies (tools/latency_sweep.py).
         // (measured: wins up to ~400 KB of positions -- 51 vs 66 us at 1e4 points -- loses beyond)
-        if (!zc && zero_copy && pos_kind != 2 && out_kind != 2 && (int64_t)p.dim * p.M * 8 <= 400 * 1024) {
+        const bool small_host = !zc && zero_copy && pos_kind != 2 && out_kind != 2 && (int64_t)p.dim * p.M * 8 <= 400 * 1024;
+        const int64_t fused_rows = small_host ? small_fused_rows(p) : 0;
+        if (fused_rows > 0) {
+            P = 1;
+            if ((rc = run_small_fused(*used[0], p, fused_rows, &L))) return rc;
+            zc = true;
+        }
+        if (!zc && small_host) {
             DeviceCtx &d0 = *used[0];
             Slot &sl = d0.slot[0];
             const int nc = p.nc();

@@ -70,7 +70,27 @@ class GsfRequest(ctypes.Structure):
     ]
 
 
+_PINNED_MIN = 256 * 1024          # below this a staging copy is cheaper than a pool round trip
+_PINNED_MAX = 1 << 30
+
 _lib = None
+_native = None   # csrc/gsf_pybind.c: native fast lane for small calls (bound in _load)
+
+
+def _bind_native(L):
+    """Native CPython binding (the counterpart of the reference's pyo3 layer): argument conversion
+    in C for small calls, where ctypes marshalling (~20 us) would dominate.  Optional -- every call
+    it declines (returns None) goes through the ctypes path below.  GSF_NATIVE_BINDING=0 disables it."""
+    global _native
+    if os.environ.get("GSF_NATIVE_BINDING", "1") == "0":
+        return
+    try:
+        from . import _gsf_native as nat
+    except ImportError:
+        return
+    addr = [ctypes.cast(getattr(L, n), _vp).value for n in ("gsf_summate", "gsf_summate_incompr", "gsf_summate_fourier")]
+    nat.bind(addr[0], addr[1], addr[2], np.ndarray, np.empty, np.float64, _PINNED_MIN)
+    _native = nat
 
 
 def _load():
@@ -129,6 +149,7 @@ def _load():
                  "gsf_shutdown"):
         getattr(L, name).restype = _int
     _lib = L
+    _bind_native(L)
     return L
 
 
@@ -185,8 +206,6 @@ class _Arr:
         return (self.ptr,) + self.strides
 
 
-_PINNED_MIN = 256 * 1024          # below this a staging copy is cheaper than a pool round trip
-_PINNED_MAX = 1 << 30
 
 
 def _result_array(shape, order="C"):
@@ -230,6 +249,12 @@ def _check_shapes(cov, z1, z2, pos):
 def summate(cov_samples, z1, z2, pos, num_threads=None):
     """Scalar randomization method (reference: summate_py, src/lib.rs:33-48 -> field::summator)."""
     L = _load()
+    if _native is not None:
+        r = _native.summate(cov_samples, z1, z2, pos, num_threads)
+        if r.__class__ is np.ndarray:
+            return r
+        if r is not None:
+            _raise(r)
     cov, a1, a2, p = _Arr(cov_samples, 2, "cov_samples"), _Arr(z1, 1, "z1"), _Arr(z2, 1, "z2"), _Arr(pos, 2, "pos")
     _check_shapes(cov, a1, a2, p)
     if p.device:
@@ -249,6 +274,12 @@ def summate_incompr(cov_samples, z1, z2, pos, num_threads=None):
 
     Returns shape (d, M) in Fortran order, like the reference (src/field.rs:166-174)."""
     L = _load()
+    if _native is not None:
+        r = _native.summate_incompr(cov_samples, z1, z2, pos, num_threads)
+        if r.__class__ is np.ndarray:
+            return r
+        if r is not None:
+            _raise(r)
     cov, a1, a2, p = _Arr(cov_samples, 2, "cov_samples"), _Arr(z1, 1, "z1"), _Arr(z2, 1, "z2"), _Arr(pos, 2, "pos")
     _check_shapes(cov, a1, a2, p)
     if p.device:
@@ -266,6 +297,12 @@ def summate_incompr(cov_samples, z1, z2, pos, num_threads=None):
 def summate_fourier(spectrum_factor, modes, z1, z2, pos, num_threads=None):
     """Periodic Fourier method (reference: summate_fourier_py, src/lib.rs:67-84)."""
     L = _load()
+    if _native is not None:
+        r = _native.summate_fourier(spectrum_factor, modes, z1, z2, pos, num_threads)
+        if r.__class__ is np.ndarray:
+            return r
+        if r is not None:
+            _raise(r)
     sf = _Arr(spectrum_factor, 1, "spectrum_factor")
     cov, a1, a2, p = _Arr(modes, 2, "modes"), _Arr(z1, 1, "z1"), _Arr(z2, 1, "z2"), _Arr(pos, 2, "pos")
     _check_shapes(cov, a1, a2, p)
