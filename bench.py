@@ -327,11 +327,14 @@ def run_ours(args):
 
     def timed_calls(fn, arrays, k, warm):
         nonlocal e2e_launches
+        # warm up the way the timed loop runs: the previous result stays alive while the next call
+        # allocates its own, so two result blocks alternate in the library's pinned pool (a first-time
+        # cudaMallocHost of an 800 MB result costs ~0.4 s and is not part of the steady state)
+        res = None
         for i in range(warm):
-            fn(*margs, arrays[i % len(arrays)])
+            res = fn(*margs, arrays[i % len(arrays)])
         barrier()
         t0 = time.perf_counter()
-        res = None
         for i in range(k):
             res = fn(*margs, arrays[i % len(arrays)])
         torch.cuda.synchronize()
@@ -486,14 +489,15 @@ def c2_block(gc, workloads, torch, timed_calls_factory, world):
     del dpos, dout
 
     def host_ms(arrays, k_steps):
+        r = None
         for i in range(5):
-            gc.summate(k, z1, z2, arrays[i % len(arrays)])
+            r = gc.summate(k, z1, z2, arrays[i % len(arrays)])
         reps = []
         for _ in range(3):
             barrier()
             t0 = time.perf_counter()
             for i in range(k_steps):
-                gc.summate(k, z1, z2, arrays[i % len(arrays)])
+                r = gc.summate(k, z1, z2, arrays[i % len(arrays)])
             reps.append(max_over_ranks((time.perf_counter() - t0) * 1e3) / k_steps)
         return sorted(reps)[1], reps
 
@@ -581,7 +585,8 @@ def in_process_block(gc, workloads, args, world):
     a = w["args"]
     gc.set_grid_detection(False)
     gc.set_devices(list(range(world)))
-    fn(*a)                                            # warm-up (allocates the per-device rings)
+    many = fn(*a)                                     # warm-up (allocates the per-device rings)
+    many = fn(*a)                                     # ... and the second result block of the steady state
     times = []
     for _ in range(3):
         t0 = time.perf_counter()

@@ -11,6 +11,7 @@
 // steps, device-resident memory skips the copies.  With several devices configured the points are
 // sharded contiguously, one host thread per device, no collective.
 #include <cuda_runtime.h>
+#include <sched.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -180,6 +181,10 @@ struct DeviceCtx {
     int64_t rec_n = -1;
     double rec_scale = 0.0;
     bool rec_valid = false;
+    // raw modes of the last one-launch small call (see small_modes_repeat)
+    std::vector<double> small_seen;
+    int small_kind = -1, small_dim = 0;
+    double small_scale = 0.0;
     double *g_axes = nullptr, *g_E0 = nullptr, *g_E1 = nullptr, *g_F = nullptr;   // grid-path tables
     size_t g_axes_cap = 0, g_E0_cap = 0, g_E1_cap = 0, g_F_cap = 0;
     double *ring_in = nullptr, *ring_out = nullptr;   // pinned staging rings of the chunk pipeline
@@ -441,7 +446,9 @@ void choose_variant(const DeviceCtx &d, const Problem &p, int64_t m_launch, bool
     // a pipelined chunk is followed by the next chunk's kernel on another stream, which fills the
     // SMs as this one drains: long tiles pay off from much smaller launches
     if (m_launch >= (pipelined ? 120000 : 750000)) {
-        bestP = 3;
+        // (3-D incompressible: P = 4 measured +1.2 % over P = 3 with the degree-5 polynomial,
+        //  tools/variant_p_probe.py; every other kind is best at 3)
+        bestP = inc && p.dim == 3 && p.deg == gsf::kFastDeg ? 4 : 3;
     } else if (ctas1 < 2 * d.sm_count && !pipelined) {
         // (pipelined chunks never split the modes: neighbouring chunks' kernels fill the machine,
         //  and L = 1 keeps every point's summation order independent of chunking / device count)
@@ -706,6 +713,39 @@ int64_t small_fused_rows(const Problem &p)
     if (p.kind == gsf::kFourier && p.mem_sf != 0 && p.mem_sf != 1) return 0;
     const int64_t rows = (p.dim + 2 + (p.kind == gsf::kFourier ? 1 : 0)) * p.N;
     return rows <= kSmallCapB ? rows : 0;
+}
+
+// The one-launch kernel rebuilds the mode records in every CTA, which is the cheapest thing to do
+// for modes seen once (ensembles: fresh z1/z2 per call).  A caller that evaluates the SAME modes
+// again (one field, new positions) is better served by records cached on the device and the plain
+// kernel (gsf_prep_modes only once).  So: modes identical to the cached records, or seen for the
+// second time in a row, take the cached-record path; anything else stays on the one-launch kernel.
+bool small_modes_repeat(DeviceCtx &d, const Problem &p)
+{
+    const int rows = p.dim + 2 + (p.kind == gsf::kFourier ? 1 : 0);
+    const int64_t N = p.N;
+    static thread_local std::vector<double> h;
+    h.resize((size_t)rows * N);
+    for (int dd = 0; dd < p.dim; ++dd)
+        for (int64_t i = 0; i < N; ++i) h[(size_t)dd * N + i] = p.k[dd * p.ks0 + i * p.ks1];
+    for (int64_t i = 0; i < N; ++i) h[(size_t)p.dim * N + i] = p.z1[i * p.z1s];
+    for (int64_t i = 0; i < N; ++i) h[(size_t)(p.dim + 1) * N + i] = p.z2[i * p.z2s];
+    if (p.kind == gsf::kFourier)
+        for (int64_t i = 0; i < N; ++i) h[(size_t)(p.dim + 2) * N + i] = p.sf[i * p.sfs];
+    const double af = gsf::amp_factor(p.deg);
+    const double scale = af == 1.0 ? p.scale : p.scale * af;
+    const size_t bytes = h.size() * sizeof(double);
+    if (d.rec_valid && d.rec_kind == p.kind && d.rec_dim == p.dim && d.rec_n == N && d.rec_scale == scale &&
+        d.rec_src.size() == h.size() && memcmp(d.rec_src.data(), h.data(), bytes) == 0)
+        return true;
+    if (d.small_kind == p.kind && d.small_dim == p.dim && d.small_scale == scale && d.small_seen.size() == h.size() &&
+        memcmp(d.small_seen.data(), h.data(), bytes) == 0)
+        return true;
+    d.small_seen = h;
+    d.small_kind = p.kind;
+    d.small_dim = p.dim;
+    d.small_scale = scale;
+    return false;
 }
 
 int run_small_fused(DeviceCtx &d, const Problem &p, int64_t rows, int *L_used)
@@ -1271,12 +1311,14 @@ int run_host_call(Problem p, const GridSpec *grid)
     }
     // do not spread tiny problems: at least 2^16 points per device
     int G = (int)devs.size();
+    const bool one_device_process = G == 1 && pos_kind != 2 && out_kind != 2;
     G = (int)std::max<int64_t>(1, std::min<int64_t>(G, p.M / 65536));
     devs.resize(G);
 
     std::vector<DeviceCtx *> used(G);
     for (int g = 0; g < G; ++g)
         if ((rc = get_device_ctx(devs[g], &used[g]))) return rc;
+    if (one_device_process) bind_rank_to_gpu_node(devs[0]);   // one process per GPU: stay on the GPU's NUMA node
 
     g_trace.mark("classify + device ctx");
     // ---- structured grid?  explicit request, or exact auto-detection on host-resident positions
@@ -1287,9 +1329,10 @@ int run_host_call(Problem p, const GridSpec *grid)
     // (~5 extra launches, tools/latency_sweep.py: break-even near 2e7 point*modes) and when the
     // per-axis tables stay small next to HBM.
     // (the exact check is one long memory-bound pass: unlike the per-chunk staging copies it
-    //  does profit from many threads)
-    const int detect_threads = std::max(threads1, std::min(8, (int)std::thread::hardware_concurrency() /
-                                                                   (2 * std::max(1, local_world_size()))));
+    //  does profit from many threads: one per 2 MB of positions, up to half this rank's cores)
+    const int64_t pos_mb = grid ? 0 : (int64_t)p.dim * p.M * 8 / (2 << 20);
+    const int detect_threads = std::max<int>(threads1, (int)std::min<int64_t>(std::min<int64_t>(32, std::max<int64_t>(1, pos_mb)),
+                                             (int64_t)std::max(1, cores_per_pipeline(1) / 2)));
     // Speculation: the candidate structure (axis lengths from the first change of each coordinate)
     // costs microseconds; the EXACT check of all points costs a pass over the whole array.  The
     // grid kernels need only the candidate axes, so they start at once while pool workers verify;
@@ -1400,7 +1443,9 @@ int run_host_call(Problem p, const GridSpec *grid)
         // explicit H2D and D2H copies and their launch latencies (tools/latency_sweep.py).
         // (measured: wins up to ~400 KB of positions -- 51 vs 66 us at 1e4 points -- loses beyond)
         const bool small_host = !zc && zero_copy && pos_kind != 2 && out_kind != 2 && (int64_t)p.dim * p.M * 8 <= 400 * 1024;
-        const int64_t fused_rows = small_host ? small_fused_rows(p) : 0;
+        int64_t fused_rows = small_host ? small_fused_rows(p) : 0;
+        static const bool promote = []() { const char *e = getenv("GSF_SMALL_PROMOTE"); return !(e && e[0] == '0'); }();
+        if (fused_rows > 0 && promote && small_modes_repeat(*used[0], p)) fused_rows = 0;
         if (fused_rows > 0) {
             P = 1;
             if ((rc = run_small_fused(*used[0], p, fused_rows, &L))) return rc;

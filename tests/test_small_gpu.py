@@ -67,6 +67,7 @@ def test_small_path_matches_oracle_and_general_kernel(kind, d, n, m):
 
 
 def test_c1_takes_the_one_launch_path():
+    gc.shutdown()                                             # forget every cached / recently seen mode set
     w = workloads.make("c1")
     got = gc.summate(*w["args"])
     st = gc.last_stats()
@@ -129,3 +130,29 @@ def test_fresh_modes_every_call_and_repeat_identity():
         ref = oracle.summate(k, zz[0], zz[1], pos, oracle.max_threads())
         assert float(np.max(np.abs(got - ref))) <= TOL * float(np.std(ref))
     assert np.array_equal(first, gc.summate(k, z1, z2, pos))
+
+
+def test_repeated_modes_are_promoted_to_cached_records():
+    """Fresh modes (ensembles) stay on the one-launch kernel; the same modes for the second time in a
+    row go through gsf_prep_modes once and are served from the cached records afterwards.  All three
+    paths give bit-identical fields."""
+    gc.shutdown()
+    d, n, m = 2, 100, 10000
+    k, z1, z2, _ = _modes(21, d, n)
+    rng = np.random.default_rng(22)
+    pos = [rng.uniform(0, 50, size=(d, m)) for _ in range(3)]
+    raw_bytes = (d + 2) * n * 8
+    a = gc.summate(k, z1, z2, pos[0]); st_a = gc.last_stats()
+    b = gc.summate(k, z1, z2, pos[1]); st_b = gc.last_stats()
+    c = gc.summate(k, z1, z2, pos[2]); st_c = gc.last_stats()
+    assert st_a["kernel_launches"] == 1 and st_a["h2d_bytes"] == d * m * 8 + raw_bytes      # one-launch kernel
+    assert st_b["kernel_launches"] == 2                                                     # upload + pre-pass + kernel
+    assert st_c["kernel_launches"] == 1 and st_c["h2d_bytes"] == d * m * 8                  # cached records
+    for got, p in zip((a, b, c), pos):
+        ref = oracle.summate(k, z1, z2, p, oracle.max_threads())
+        assert float(np.max(np.abs(got - ref))) <= TOL * float(np.std(ref))
+    assert np.array_equal(a, gc.summate(k, z1, z2, pos[0]))                                 # cached path == one-launch path
+    z1b = z1.copy(); z1b[3] += 1.0
+    e = gc.summate(k, z1b, z2, pos[0])                                                      # new modes: one-launch kernel again
+    assert gc.last_stats()["kernel_launches"] == 1 and gc.last_stats()["h2d_bytes"] == d * m * 8 + raw_bytes
+    assert not np.array_equal(a, e)

@@ -1,0 +1,169 @@
+// launch_floor.cu -- what a "one launch + wait" call can cost at best on this box (C1-sized calls).
+//   * empty kernel: launch + cudaStreamSynchronize, parameter block of 64 B / 4 KB / 12 KB
+//   * same, completion signalled through a flag in mapped pinned memory that the CPU polls
+//     (__threadfence_system + store by the last CTA) instead of cudaStreamSynchronize
+//   * a kernel that reads 160 KB / writes 80 KB of mapped pinned memory (C1's positions / result)
+//   * memcpy of 160 KB into a pinned buffer the GPU has just read (the gather step)
+// Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o launch_floor launch_floor.cu
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+template <int N>
+struct Blob {
+    double v[N];
+};
+
+template <int N>
+__global__ void k_empty(const __grid_constant__ Blob<N> b, double *sink)
+{
+    if (b.v[0] == 123.456 && threadIdx.x == 0) sink[0] = b.v[N - 1];
+}
+
+__global__ void k_flag(unsigned *counter, volatile unsigned *host_flag, unsigned ticket)
+{
+    __shared__ unsigned last;
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        last = atomicAdd(counter, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        *counter = 0;
+        __threadfence_system();
+        *host_flag = ticket;
+    }
+}
+
+__global__ void k_touch(const double *pos, double *out, int m, unsigned *counter, volatile unsigned *host_flag,
+                        unsigned ticket)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < m) out[j] = pos[j] + pos[m + j];
+    if (!host_flag) return;
+    __shared__ unsigned last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        last = atomicAdd(counter, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        *counter = 0;
+        __threadfence_system();
+        *host_flag = ticket;
+    }
+}
+
+static double now_us()
+{
+    return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+template <class F>
+static void report(const char *what, F f, int n = 2000)
+{
+    std::vector<double> t((size_t)n);
+    for (int i = 0; i < 50; ++i) f(i);
+    for (int i = 0; i < n; ++i) {
+        const double t0 = now_us();
+        f(i + 50);
+        t[(size_t)i] = now_us() - t0;
+    }
+    std::sort(t.begin(), t.end());
+    printf("%-62s median %6.2f us   p10 %6.2f   p90 %6.2f\n", what, t[(size_t)n / 2], t[(size_t)n / 10], t[(size_t)n * 9 / 10]);
+}
+
+int main()
+{
+    cudaStream_t st;
+    cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    double *sink;
+    cudaMalloc(&sink, 8);
+    unsigned *counter;
+    cudaMalloc(&counter, 4);
+    cudaMemset(counter, 0, 4);
+    unsigned *flag;
+    cudaMallocHost(&flag, 64);
+    *flag = 0;
+    const int m = 10000;
+    double *hpos, *hout;
+    cudaMallocHost(&hpos, 2 * m * 8);
+    cudaMallocHost(&hout, m * 8);
+    std::vector<double> src(2 * m, 1.0), dst(m);
+    static Blob<8> b8;
+    static Blob<512> b512;
+    static Blob<1536> b1536;
+
+    report("empty kernel 64 B params, launch + cudaStreamSynchronize", [&](int) {
+        k_empty<8><<<313, 128, 0, st>>>(b8, sink);
+        cudaStreamSynchronize(st);
+    });
+    report("empty kernel 4 KB params, launch + cudaStreamSynchronize", [&](int) {
+        k_empty<512><<<313, 128, 0, st>>>(b512, sink);
+        cudaStreamSynchronize(st);
+    });
+    report("empty kernel 12 KB params, launch + cudaStreamSynchronize", [&](int) {
+        k_empty<1536><<<313, 128, 0, st>>>(b1536, sink);
+        cudaStreamSynchronize(st);
+    });
+    report("launch only, 64 B params (sync outside the timer)", [&](int) {
+        k_empty<8><<<313, 128, 0, st>>>(b8, sink);
+    });
+    cudaStreamSynchronize(st);
+    report("launch only, 4 KB params", [&](int) { k_empty<512><<<313, 128, 0, st>>>(b512, sink); });
+    cudaStreamSynchronize(st);
+    report("launch only, 12 KB params", [&](int) { k_empty<1536><<<313, 128, 0, st>>>(b1536, sink); });
+    cudaStreamSynchronize(st);
+    report("flag kernel: launch + CPU polls mapped flag", [&](int i) {
+        k_flag<<<313, 128, 0, st>>>(counter, flag, (unsigned)i + 1);
+        while (*(volatile unsigned *)flag != (unsigned)i + 1) __builtin_ia32_pause();
+    });
+    cudaStreamSynchronize(st);
+    report("touch kernel (160 KB in / 80 KB out, mapped): launch + sync", [&](int) {
+        k_touch<<<(m + 127) / 128, 128, 0, st>>>(hpos, hout, m, counter, nullptr, 0);
+        cudaStreamSynchronize(st);
+    });
+    report("touch kernel (mapped): launch + CPU polls flag", [&](int i) {
+        k_touch<<<(m + 127) / 128, 128, 0, st>>>(hpos, hout, m, counter, flag, (unsigned)i + 100000);
+        while (*(volatile unsigned *)flag != (unsigned)i + 100000) __builtin_ia32_pause();
+    });
+    cudaStreamSynchronize(st);
+    report("gather 160 KB -> pinned + touch kernel + sync + scatter 80 KB", [&](int) {
+        memcpy(hpos, src.data(), 2 * m * 8);
+        k_touch<<<(m + 127) / 128, 128, 0, st>>>(hpos, hout, m, counter, nullptr, 0);
+        cudaStreamSynchronize(st);
+        memcpy(dst.data(), hout, m * 8);
+    });
+    report("gather + touch kernel + poll flag + scatter", [&](int i) {
+        memcpy(hpos, src.data(), 2 * m * 8);
+        k_touch<<<(m + 127) / 128, 128, 0, st>>>(hpos, hout, m, counter, flag, (unsigned)i + 200000);
+        while (*(volatile unsigned *)flag != (unsigned)i + 200000) __builtin_ia32_pause();
+        memcpy(dst.data(), hout, m * 8);
+    });
+    cudaStreamSynchronize(st);
+    report("memcpy 160 KB pageable -> pinned just read by the GPU", [&](int) {
+        memcpy(hpos, src.data(), 2 * m * 8);
+        k_touch<<<(m + 127) / 128, 128, 0, st>>>(hpos, hout, m, counter, nullptr, 0);
+        cudaStreamSynchronize(st);
+    });
+    report("memcpy 160 KB pageable -> ordinary memory", [&](int) {
+        static std::vector<double> d2(2 * 10000);
+        memcpy(d2.data(), src.data(), 2 * m * 8);
+    });
+    // H2D / D2H through the copy engine for comparison
+    double *dpos, *dout;
+    cudaMalloc(&dpos, 2 * m * 8);
+    cudaMalloc(&dout, m * 8);
+    report("H2D 160 KB + touch kernel (device mem) + D2H 80 KB + sync", [&](int) {
+        cudaMemcpyAsync(dpos, hpos, 2 * m * 8, cudaMemcpyHostToDevice, st);
+        k_touch<<<(m + 127) / 128, 128, 0, st>>>(dpos, dout, m, counter, nullptr, 0);
+        cudaMemcpyAsync(hout, dout, m * 8, cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+    });
+    return 0;
+}
