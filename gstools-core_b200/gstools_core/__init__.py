@@ -20,6 +20,7 @@ Differences from the reference, all deliberate:
 """
 from __future__ import annotations
 
+import collections
 import ctypes
 import os
 import weakref
@@ -249,6 +250,8 @@ def _check_shapes(cov, z1, z2, pos):
 def summate(cov_samples, z1, z2, pos, num_threads=None):
     """Scalar randomization method (reference: summate_py, src/lib.rs:33-48 -> field::summator)."""
     L = _load()
+    if _auto_pin_cap:
+        _auto_pin(pos)
     if _native is not None:
         r = _native.summate(cov_samples, z1, z2, pos, num_threads)
         if r.__class__ is np.ndarray:
@@ -274,6 +277,8 @@ def summate_incompr(cov_samples, z1, z2, pos, num_threads=None):
 
     Returns shape (d, M) in Fortran order, like the reference (src/field.rs:166-174)."""
     L = _load()
+    if _auto_pin_cap:
+        _auto_pin(pos)
     if _native is not None:
         r = _native.summate_incompr(cov_samples, z1, z2, pos, num_threads)
         if r.__class__ is np.ndarray:
@@ -297,6 +302,8 @@ def summate_incompr(cov_samples, z1, z2, pos, num_threads=None):
 def summate_fourier(spectrum_factor, modes, z1, z2, pos, num_threads=None):
     """Periodic Fourier method (reference: summate_fourier_py, src/lib.rs:67-84)."""
     L = _load()
+    if _auto_pin_cap:
+        _auto_pin(pos)
     if _native is not None:
         r = _native.summate_fourier(spectrum_factor, modes, z1, z2, pos, num_threads)
         if r.__class__ is np.ndarray:
@@ -730,6 +737,67 @@ class pinned:
             pass
 
 
+# ---------------------------------------------------------------------------------------------
+# Opt-in: page-lock position arrays that come back.  GSTools ensembles evaluate many fields at the
+# SAME positions; the second time an array (same object memory, same size) is passed it is
+# registered with cudaHostRegister (a few ms, once) and from then on the GPU reads it in place --
+# no staging copy, a third of the host memory traffic.  The cache holds a reference to every
+# registered array, so its memory cannot be freed or reused while it is page-locked; least recently
+# used entries are unregistered beyond the byte budget.  Off by default (pinned memory is a scarce,
+# unswappable resource): set_auto_pin(max_mb) or GSF_AUTO_PIN_MB=<mb>.
+_AUTO_PIN_MIN = 1 << 20
+_auto_pin_cap = int(float(os.environ.get("GSF_AUTO_PIN_MB", "0")) * (1 << 20))
+_auto_pin_seen = {}                 # (ptr, nbytes) -> sightings of not-yet-registered arrays
+_auto_pin_live = collections.OrderedDict()   # (ptr, nbytes) -> pinned handle (LRU order)
+_auto_pin_bytes = 0
+
+
+def set_auto_pin(max_mb=0):
+    """Byte budget (MiB) of automatically page-locked position arrays; 0 switches the feature off and
+    releases everything it holds."""
+    global _auto_pin_cap
+    _auto_pin_cap = int(float(max_mb) * (1 << 20))
+    _auto_pin_trim()
+    if _auto_pin_cap == 0:
+        _auto_pin_seen.clear()
+
+
+def _auto_pin_trim():
+    global _auto_pin_bytes
+    while _auto_pin_live and _auto_pin_bytes > _auto_pin_cap:
+        (_, nbytes), handle = _auto_pin_live.popitem(last=False)
+        handle.release()
+        _auto_pin_bytes -= nbytes
+
+
+def _auto_pin(pos):
+    """Called with the `pos` argument of a host call when the feature is on."""
+    global _auto_pin_bytes
+    if not isinstance(pos, np.ndarray) or pos.dtype != np.float64 or not pos.flags.c_contiguous:
+        return
+    nbytes = pos.nbytes
+    if nbytes < _AUTO_PIN_MIN or nbytes > _auto_pin_cap:
+        return
+    key = (pos.ctypes.data, nbytes)
+    if key in _auto_pin_live:
+        _auto_pin_live.move_to_end(key)
+        return
+    n = _auto_pin_seen.get(key, 0) + 1
+    if n < 2:
+        if len(_auto_pin_seen) > 64:
+            _auto_pin_seen.clear()
+        _auto_pin_seen[key] = n
+        return
+    _auto_pin_seen.pop(key, None)
+    try:
+        handle = pinned(pos)
+    except Exception:
+        return                      # registration refused (limits): keep staging
+    _auto_pin_live[key] = handle
+    _auto_pin_bytes += nbytes
+    _auto_pin_trim()
+
+
 def set_profiling(enabled=True):
     """False/0 off, True/1 per call, 2 accumulate kernel_ms over all calls until the next set_profiling."""
     _load().gsf_set_profiling(int(enabled))
@@ -762,4 +830,7 @@ def dmma_peak(device=0, min_ms=200.0):
 
 
 def shutdown():
+    cap = _auto_pin_cap
+    set_auto_pin(0)                   # unregister automatically page-locked arrays
+    set_auto_pin(cap / (1 << 20))
     _load().gsf_shutdown()

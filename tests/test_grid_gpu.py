@@ -235,3 +235,33 @@ def test_device_resident_grid_detection():
     torch.cuda.synchronize()
     assert gc.last_stats()["grid_path"] == 0
     assert rel_err(out.cpu().numpy(), ref) <= TOL
+
+
+@pytest.mark.parametrize("shape,n", [((50, 40, 100), 1000),      # 63 row tiles x 63 K blocks
+                                     ((3, 21, 300), 1000),       # 2 row tiles x 3 column blocks: 16-way split
+                                     ((90, 130), 250),           # 2-D, 3 row tiles, two column blocks
+                                     ((7, 9, 40), 40)])          # 3 K blocks only
+def test_mode_split_launches_are_exact_and_deterministic(shape, n):
+    """Small grids split the modes over grid.z; the last-arriving CTA of a tile adds the partial sums in
+    split order.  The result must not depend on arrival order (bit-identical repeats, self-resetting
+    tickets) and must match the oracle."""
+    d = len(shape)
+    axes = [np.sort(np.random.default_rng(3 + i).uniform(0, 60, s)) for i, s in enumerate(shape)]
+    k, z1, z2, _ = modes(31, d, n, heavy=True)
+    pos = expand(axes)
+    ref = oracle.summate(k, z1, z2, pos, oracle.max_threads())
+    first = gc.summate_grid(k, z1, z2, axes)
+    assert gc.last_stats()["grid_path"] == 2
+    assert rel_err(first, ref) <= TOL
+    for _ in range(4):
+        assert np.array_equal(first, gc.summate_grid(k, z1, z2, axes))
+    refi = oracle.summate_incompr(k, z1, z2, pos, oracle.max_threads())
+    goti = gc.summate_incompr_grid(k, z1, z2, axes)
+    assert rel_err(goti, refi) <= TOL
+    assert np.array_equal(goti, gc.summate_incompr_grid(k, z1, z2, axes))
+    # device-resident result: one launch over all rows
+    import torch
+    out = torch.empty(pos.shape[1], dtype=torch.float64, device="cuda")
+    gc.summate_grid(k, z1, z2, axes, out=out)
+    torch.cuda.synchronize()
+    assert rel_err(out.cpu().numpy(), ref) <= TOL

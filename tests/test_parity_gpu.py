@@ -447,3 +447,32 @@ def test_mode_record_cache_invalidation():
     assert np.max(np.abs(d - 3.0 * b)) <= 1e-12 * np.std(b)
     e = gc.summate(k, z1, z2, pos)
     assert np.array_equal(e, b)
+
+
+def test_auto_pin_of_repeated_position_arrays():
+    """Opt-in (set_auto_pin / GSF_AUTO_PIN_MB): a position array passed for the second time is page-locked
+    and read in place from then on; same results, in-place edits are seen, switching off releases it."""
+    k, z1, z2, pos = _rand(81, 3, 300, 200_000)
+    ref = gc.summate(k, z1, z2, pos)
+    assert gc.last_stats()["pos_memory"] == 0
+    gc.set_auto_pin(64)
+    try:
+        a = gc.summate(k, z1, z2, pos)                       # first sighting: still staged
+        assert gc.last_stats()["pos_memory"] == 0
+        b = gc.summate(k, z1, z2, pos)                       # second: registered, read in place
+        assert gc.last_stats()["pos_memory"] == 1
+        assert np.array_equal(a, ref) and np.array_equal(b, ref)
+        pos[:, 1000:2000] += 0.25                            # in-place edit of a pinned array
+        c = gc.summate(k, z1, z2, pos)
+        assert gc.last_stats()["pos_memory"] == 1
+        assert rel_err(c, oracle.summate(k, z1, z2, pos, oracle.max_threads())) <= TOL
+        other = pos.copy()                                   # budget: 64 MB holds both (4.8 MB each)
+        gc.summate(k, z1, z2, other); gc.summate(k, z1, z2, other)
+        assert gc.last_stats()["pos_memory"] == 1
+        gc.set_auto_pin(6)                                   # shrink: the least recently used one goes
+        gc.summate(k, z1, z2, pos)
+        assert gc.last_stats()["pos_memory"] == 0
+    finally:
+        gc.set_auto_pin(0)
+    d = gc.summate(k, z1, z2, pos)
+    assert gc.last_stats()["pos_memory"] == 0 and np.array_equal(c, d)
