@@ -392,12 +392,16 @@ def run_ours(args):
         return
 
     peaks = peak_file()
-    traffic = None
-    try:   # DRAM bytes per launch from the committed ncu --set full capture of this kernel / workload
-        with open(os.path.join(ROOT, "profiles", "ncu_r2_%s_traffic.json" % args.workload)) as f:
-            t = json.load(f)
-        if world == 1 and args.scale == 1.0:
-            traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
+    # DRAM bytes per launch from the committed ncu captures of this kernel: the capture whose launch
+    # (points x modes) is the one timed here (N = 1: the whole workload; N ranks: one shard)
+    traffic, traffic_src = None, None
+    try:
+        import glob
+        for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_r2_*_traffic.json"))):
+            with open(path) as f:
+                t = json.load(f)
+            if t.get("modes") == n and abs(t.get("points_per_launch", -1) - m) <= 0.01 * m:
+                traffic, traffic_src = t["dram_bytes_read"] + t["dram_bytes_write"], os.path.relpath(path, ROOT)
     except Exception:
         traffic = None
     w_exec = variant["fp64_slots"]
@@ -424,6 +428,7 @@ def run_ours(args):
             "bound": "fp64", "achieved": ach_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
             "frac": ach_tflops / peak_tflops, "traffic": traffic,
             "traffic_unit": "bytes of DRAM per launch (ncu dram__bytes_read+write); algorithmic bytes: %d" % (pos_bytes + out_bytes),
+            "traffic_source": traffic_src,
             "kernel": "gsf_sum_kernel<D=%d,NC=%d,P=%d,L=%d,DEG=%d>" % (d, nc, variant["points_per_thread"],
                                                                       variant["lanes_per_point"], variant["poly_degree"]),
             "kernel_ms": kernel_ms, "timed": "library CUDA events around every launch, same loop as ms_per_step",

@@ -170,3 +170,40 @@ def test_variograms_fail_loudly_without_device():
         gc.variogram_unstructured(f, edges, pos)
     with pytest.raises(RuntimeError, match="no CUDA device"):
         gc.variogram_directional(f, edges, pos, np.array([[1.0, 0.0]]))
+
+
+def test_native_binding_fast_lane_and_its_fallbacks():
+    """csrc/gsf_pybind.c: the native CPython binding handles plain float64 ndarrays with small results
+    and declines (None) everything else, so that the ctypes path raises the reference-shaped errors."""
+    gc._load()
+    nat = gc._native
+    assert nat is not None, "native binding not built (make -C gstools-core_b200/csrc)"
+    k, z1, z2, pos = np.random.rand(2, 10), np.random.rand(10), np.random.rand(10), np.random.rand(2, 50)
+    sf = np.random.rand(10)
+    # declined: wrong dtype / not an ndarray / shape mismatch / rank mismatch / result beyond the fast lane
+    assert nat.summate(k.astype(np.float32), z1, z2, pos, None) is None
+    assert nat.summate([[1.0]], z1, z2, pos, None) is None
+    assert nat.summate(k, z1[:5], z2, pos, None) is None
+    assert nat.summate(k, z1, z2, pos[0], None) is None
+    assert nat.summate(k, z1, z2, np.random.rand(2, 40000), None) is None
+    assert nat.summate_fourier(sf[:3], k, z1, z2, pos, None) is None
+    assert nat.summate(k, z1, z2, np.zeros((2, 0)), None) is None
+    with pytest.raises(OverflowError):
+        nat.summate(k, z1, z2, pos, -1)
+    with pytest.raises(TypeError):
+        nat.summate(k, z1, z2)
+    # handled: strided views are fine; without a device the C ABI's status comes back as an int
+    r = nat.summate(k[:, ::2], z1[::2], z2[::2], np.asfortranarray(pos), 4)
+    if gc.device_count() == 0:
+        assert r == 4                                     # GSF_ERR_NO_DEVICE
+        for fn, a in ((gc.summate, (k, z1, z2, pos)), (gc.summate_incompr, (k, z1, z2, pos)),
+                      (gc.summate_fourier, (sf, k, z1, z2, pos))):
+            with pytest.raises(RuntimeError, match="no CUDA device"):
+                fn(*a)
+    else:
+        assert isinstance(r, np.ndarray) and r.shape == (50,)
+    # the reference-shaped errors still come from the general path
+    with pytest.raises(TypeError):
+        gc.summate(k.astype(np.float32), z1, z2, pos)
+    with pytest.raises(ValueError):
+        gc.summate(k, z1[:5], z2, pos)
