@@ -1331,8 +1331,11 @@ int run_host_call(Problem p, const GridSpec *grid)
     // (the exact check is one long memory-bound pass: unlike the per-chunk staging copies it
     //  does profit from many threads: one per 2 MB of positions, up to half this rank's cores)
     const int64_t pos_mb = grid ? 0 : (int64_t)p.dim * p.M * 8 / (2 << 20);
+    //  (inputs of hundreds of MB -- C4, C5 -- may take three quarters of them: with several GPUs the
+    //   check, not the GEMM, is what the caller waits for)
+    const int core_share = pos_mb >= 128 ? cores_per_pipeline(1) * 3 / 4 : cores_per_pipeline(1) / 2;
     const int detect_threads = std::max<int>(threads1, (int)std::min<int64_t>(std::min<int64_t>(32, std::max<int64_t>(1, pos_mb)),
-                                             (int64_t)std::max(1, cores_per_pipeline(1) / 2)));
+                                             (int64_t)std::max(1, core_share)));
     // Speculation: the candidate structure (axis lengths from the first change of each coordinate)
     // costs microseconds; the EXACT check of all points costs a pass over the whole array.  The
     // grid kernels need only the candidate axes, so they start at once while pool workers verify;
