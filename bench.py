@@ -509,6 +509,13 @@ def c2_block(gc, workloads, torch, timed_calls_factory, world):
     h0, h1 = gc.pinned(pages[0]), gc.pinned(pages[1])
     pin_ms, pin_reps = host_ms(pages, 50)
     h0.release(); h1.release()
+    # opt-in auto-pin (gstools_core.set_auto_pin): the plain call on the same pageable arrays; the
+    # library page-locks a position array the second time it sees it (registration happens in the
+    # warm-up calls) and reads it in place from then on
+    gc.set_auto_pin(256)
+    auto_ms, auto_reps = host_ms(pages, 50)
+    auto_mem = gc.last_stats()["pos_memory"]
+    gc.set_auto_pin(0)
     out = {
         "workload": WORKLOADS["c2"][0] + " per rank (weak)",
         "kernel": {"value": world * pm / (dev_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": dev_ms, "kernel_ms": kernel_ms,
@@ -518,7 +525,14 @@ def c2_block(gc, workloads, torch, timed_calls_factory, world):
                          "staging_threads": st["staging_threads"]},
         "e2e_pinned": {"value": world * pm / (pin_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": pin_ms,
                        "repetitions_ms_per_step": pin_reps},
+        "e2e_pageable_auto_pin": {"value": world * pm / (auto_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": auto_ms,
+                                  "repetitions_ms_per_step": auto_reps, "pos_memory_seen_by_library": auto_mem,
+                                  "note": "opt-in set_auto_pin(256 MB): repeated position arrays are page-locked in place"},
     }
+    if world > 1:
+        out["note"] = ("%d ranks x (24 MB in + 8 MB out) per %.2f ms of kernel = %.0f GB/s of host DRAM traffic wanted from ONE host: "
+                       "this weak block is bound by the host's memory system, not by the GPUs (profiles/scaling_r2.md)"
+                       % (world, kernel_ms, world * 32e6 / (kernel_ms * 1e-3) / 1e9))
     if world == 1:
         # default API on this gridded input (exact grid detection on): the structured-grid GEMM path
         gc.set_grid_detection(True)

@@ -1718,6 +1718,17 @@ int gsf_debug_chunk_schedule(int64_t n_points, int64_t forced_chunk, int64_t *si
     return (int)v.size() > max_sizes ? -(int)v.size() : n;
 }
 
+int gsf_debug_parse_cpulist(const char *list, int *cpus, int max_cpus)
+{
+    if (!list || (max_cpus > 0 && !cpus)) return fail(GSF_ERR_ARG, "bad arguments");
+    cpu_set_t set;
+    const int n = parse_cpulist(list, &set);
+    int w = 0;
+    for (int c = 0; c < CPU_SETSIZE && w < max_cpus; ++c)
+        if (CPU_ISSET(c, &set)) cpus[w++] = c;
+    return n;
+}
+
 int gsf_debug_detect_grid(int dim, int64_t n_points, const double *pos, int64_t pos_s0, int64_t pos_s1,
                           int64_t *axis_n)
 {

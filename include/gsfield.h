@@ -194,6 +194,9 @@ int gsf_debug_variogram_thresholds(double edge, double angles_tol, double *sqrt_
  * host-resident points (returns the count, or -count if max_sizes is too small), and the exact
  * structured-grid detector (returns 1 and the axis lengths, or 0). */
 int gsf_debug_chunk_schedule(int64_t n_points, int64_t forced_chunk, int64_t *sizes, int max_sizes);
+/* The sysfs cpulist parser behind the rank-to-NUMA-node binding ("0-15,64-79"): writes up to max_cpus
+ * cpu ids in increasing order, returns how many the list names. */
+int gsf_debug_parse_cpulist(const char *list, int *cpus, int max_cpus);
 int gsf_debug_detect_grid(int dim, int64_t n_points, const double *pos, int64_t pos_s0, int64_t pos_s1,
                           int64_t *axis_n);
 

@@ -115,3 +115,22 @@ def test_variogram_acos_threshold_is_exact():
         assert nxt >= 1.0 or math.acos(nxt) < tol
     assert _thresholds(1.0, 2.0)[1] == -1.0            # acos(a) <= pi/2 < tol for every a >= 0: never rejected
     assert _thresholds(1.0, 1e-300)[1] == float(np.nextafter(1.0, 0.0))
+
+
+def test_cpulist_parser_of_the_numa_binding():
+    """bind_rank_to_gpu_node reads /sys/bus/pci/devices/<gpu>/local_cpulist; its parser on the formats sysfs prints."""
+    L.gsf_debug_parse_cpulist.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_int), ctypes.c_int]
+    L.gsf_debug_parse_cpulist.restype = ctypes.c_int
+
+    def parse(text):
+        buf = (ctypes.c_int * 1024)()
+        n = L.gsf_debug_parse_cpulist(text.encode(), buf, 1024)
+        return list(buf[:n])
+
+    assert parse("0-3") == [0, 1, 2, 3]
+    assert parse("0-15,64-79\n") == list(range(16)) + list(range(64, 80))
+    assert parse("5") == [5]
+    assert parse("1,3,5-6") == [1, 3, 5, 6]
+    assert parse("2-2,2") == [2]
+    assert parse("") == [] and parse("\n") == []
+    assert parse("0-1,x") == [0, 1]

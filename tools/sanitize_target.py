@@ -13,6 +13,14 @@ for d in (1, 2, 3, 5):
         gc.set_variant(P, L); gc.summate(k, z1, z2, pos)
         if d in (2, 3): gc.summate_incompr(k, z1, z2, pos)
 gc.set_variant(0, 0)
+# one-launch small path (gsf_small_kernel, both parameter-block sizes, several lane counts), then the
+# repeat-mode promotion to cached records
+for d, n, m in ((1, 60, 300), (2, 100, 10000), (3, 200, 2500), (3, 256, 64), (2, 33, 700)):
+    k, z1, z2 = modes(d, n)
+    pos = rng.uniform(0, 9, size=(d, m))
+    gc.summate(k, z1, z2, pos); gc.summate_fourier(np.abs(z1), k, z1, z2, pos)
+    if d in (2, 3): gc.summate_incompr(k, z1, z2, pos)
+    gc.summate(k, z1, z2, pos); gc.summate(k, z1, z2, pos)
 k, z1, z2 = modes(3, 700)
 gc.set_chunk_points(1024); gc.summate(k, z1, z2, rng.uniform(0, 9, size=(3, 5000))); gc.set_chunk_points(0)
 gc.summate(k, z1, z2, rng.uniform(0, 9, size=(3, 400000)))          # hybrid tail tiles (P = 3)
