@@ -156,3 +156,35 @@ def test_repeated_modes_are_promoted_to_cached_records():
     e = gc.summate(k, z1b, z2, pos[0])                                                      # new modes: one-launch kernel again
     assert gc.last_stats()["kernel_launches"] == 1 and gc.last_stats()["h2d_bytes"] == d * m * 8 + raw_bytes
     assert not np.array_equal(a, e)
+
+
+def test_concurrent_python_threads():
+    """The native binding releases the GIL around the C call; the library serialises calls on its
+    context mutex.  Four threads mixing C1-sized, mid-sized and incompressible calls must all get the
+    single-threaded answers."""
+    import threading
+    cases = []
+    for i, (kind, d, n, m) in enumerate([("summate", 2, 100, 10000), ("summate", 3, 300, 60000),
+                                         ("summate_incompr", 3, 64, 4000), ("summate_fourier", 2, 200, 9000)]):
+        k, z1, z2, sf = _modes(100 + i, d, n)
+        pos = np.random.default_rng(200 + i).uniform(0, 30, size=(d, m))
+        args = (sf, k, z1, z2, pos) if kind == "summate_fourier" else (k, z1, z2, pos)
+        cases.append((kind, args, getattr(gc, kind)(*args)))
+    errors = []
+
+    def worker(idx):
+        try:
+            for it in range(25):
+                kind, args, want = cases[(idx + it) % len(cases)]
+                got = getattr(gc, kind)(*args)
+                if not np.array_equal(got, want):
+                    errors.append("thread %d iteration %d: %s differs" % (idx, it, kind))
+        except Exception as exc:                      # noqa: BLE001
+            errors.append("thread %d: %r" % (idx, exc))
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:5]
