@@ -748,6 +748,30 @@ bool small_modes_repeat(DeviceCtx &d, const Problem &p)
     return false;
 }
 
+// One launch over device-visible memory (q.pos / q.out are device or mapped host pointers), then wait:
+// run_shard's single-chunk case without the chunk schedule, the staging crew and its bookkeeping
+// (small calls count microseconds).
+int run_single_launch(DeviceCtx &d, const Problem &q, int *P_used, int *L_used)
+{
+    GSF_CUDA(cudaSetDevice(d.dev));
+    reset_call_counters(d);
+    DrainOnError guard(d);
+    cudaStream_t s0 = d.slot[0].stream;
+    int rc;
+    if (d.ws_used) GSF_CUDA(cudaStreamWaitEvent(s0, d.ev_ws, 0));
+    if ((rc = prepare_modes(d, q, s0, gsf::amp_factor(q.deg)))) return rc;
+    g_trace.mark("single: prepare modes");
+    choose_variant(d, q, q.M, false, P_used, L_used);
+    if ((rc = launch_sum(d, q, q.pos, q.ps0, q.ps1, q.out, q.os0, q.os1, q.M, s0, *P_used, *L_used))) return rc;
+    g_trace.mark("single: launched");
+    GSF_CUDA(cudaStreamSynchronize(s0));
+    g_trace.mark("single: synced");
+    d.chunks = 1;
+    d.ws_used = false;
+    guard.armed = false;
+    return GSF_OK;
+}
+
 int run_small_fused(DeviceCtx &d, const Problem &p, int64_t rows, int *L_used)
 {
     GSF_CUDA(cudaSetDevice(d.dev));
@@ -760,7 +784,7 @@ int run_small_fused(DeviceCtx &d, const Problem &p, int64_t rows, int *L_used)
     OutLayout lay;
     lay.aos = nc > 1 && p.os0 == 1 && p.os1 == nc;
     lay.direct = false;
-    gather_pos_part(p, 0, p.M, 0, p.M, sl.h_pos, true);
+    gather_pos_part(p, 0, p.M, 0, p.M, sl.h_pos, false);   // streaming stores: the GPU read this buffer last (3 us less than memcpy, tools/micro/launch_floor.cu)
     g_trace.mark("small: gather pos");
     // lanes per point: as choose_variant -- widen until every SM has two CTAs, >= 32 modes per lane
     int L = 1;
@@ -1464,27 +1488,22 @@ int run_host_call(Problem p, const GridSpec *grid)
             cudaSetDevice(d0.dev);
             if (!(rc = ensure_cap(&sl.h_pos, &sl.h_pos_cap, (size_t)p.dim * p.M, true)) &&
                 !(rc = ensure_cap(&sl.h_out, &sl.h_out_cap, (size_t)nc * p.M, true))) {
-                void *dpos = nullptr, *dout = nullptr;
-                if (cudaHostGetDevicePointer(&dpos, sl.h_pos, 0) == cudaSuccess &&
-                    cudaHostGetDevicePointer(&dout, sl.h_out, 0) == cudaSuccess) {
-                    gather_pos_part(p, 0, p.M, 0, p.M, sl.h_pos, true);
-                    g_trace.mark("small: gather pos");
-                    Problem q = p;
-                    q.pos = static_cast<const double *>(dpos); q.ps0 = p.M; q.ps1 = 1;
-                    q.out = static_cast<double *>(dout);
-                    if (nc == 1) { q.os0 = 0; q.os1 = 1; }
-                    else if (lay.aos) { q.os0 = 1; q.os1 = nc; }
-                    else { q.os0 = p.M; q.os1 = 1; }
-                    q.zero_copy = true;
-                    rc = run_shard(d0, q, 0, p.M, 2, 2, &P, &L, threads1);
-                    if (!rc) scatter_out_part(p, lay, 0, p.M, 0, p.M, sl.h_out, true);
-                    g_trace.mark("small: scatter out");
-                    d0.h2d_bytes += (int64_t)p.dim * p.M * 8;
-                    d0.d2h_bytes += (int64_t)nc * p.M * 8;
-                    zc = true;
-                } else {
-                    cudaGetLastError();
-                }
+                // (cudaMallocHost memory: under UVA the device address equals the host address)
+                gather_pos_part(p, 0, p.M, 0, p.M, sl.h_pos, false);   // streaming stores: the GPU read this buffer last (3 us less than memcpy, tools/micro/launch_floor.cu)
+                g_trace.mark("small: gather pos");
+                Problem q = p;
+                q.pos = sl.h_pos; q.ps0 = p.M; q.ps1 = 1;
+                q.out = sl.h_out;
+                if (nc == 1) { q.os0 = 0; q.os1 = 1; }
+                else if (lay.aos) { q.os0 = 1; q.os1 = nc; }
+                else { q.os0 = p.M; q.os1 = 1; }
+                q.zero_copy = true;
+                rc = run_single_launch(d0, q, &P, &L);
+                if (!rc) scatter_out_part(p, lay, 0, p.M, 0, p.M, sl.h_out, true);
+                g_trace.mark("small: scatter out");
+                d0.h2d_bytes += (int64_t)p.dim * p.M * 8;
+                d0.d2h_bytes += (int64_t)nc * p.M * 8;
+                zc = true;
             }
             if (rc) return rc;
         }

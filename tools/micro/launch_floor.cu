@@ -4,7 +4,7 @@
 //     (__threadfence_system + store by the last CTA) instead of cudaStreamSynchronize
 //   * a kernel that reads 160 KB / writes 80 KB of mapped pinned memory (C1's positions / result)
 //   * memcpy of 160 KB into a pinned buffer the GPU has just read (the gather step)
-// Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o launch_floor launch_floor.cu
+// Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o launch_floor launch_floor.cu ../../gstools-core_b200/csrc/gsf_hostcopy.o
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -12,6 +12,8 @@
 #include <cstdio>
 #include <cstring>
 #include <vector>
+
+extern "C" void gsf_copy_stream(double *dst, const double *src, size_t n);   // AVX2 streaming stores (csrc/gsf_hostcopy.cpp)
 
 template <int N>
 struct Blob {
@@ -151,6 +153,27 @@ int main()
         k_touch<<<(m + 127) / 128, 128, 0, st>>>(hpos, hout, m, counter, nullptr, 0);
         cudaStreamSynchronize(st);
     });
+    report("streaming-store copy 160 KB pageable -> pinned just read by the GPU", [&](int) {
+        gsf_copy_stream(hpos, src.data(), 2 * m);
+        k_touch<<<(m + 127) / 128, 128, 0, st>>>(hpos, hout, m, counter, nullptr, 0);
+        cudaStreamSynchronize(st);
+    });
+    report("streaming-store gather + touch kernel + sync + scatter 80 KB", [&](int) {
+        gsf_copy_stream(hpos, src.data(), 2 * m);
+        k_touch<<<(m + 127) / 128, 128, 0, st>>>(hpos, hout, m, counter, nullptr, 0);
+        cudaStreamSynchronize(st);
+        memcpy(dst.data(), hout, m * 8);
+    });
+    {   // two pinned input buffers used alternately (the GPU read the OTHER one last)
+        double *hpos2;
+        cudaMallocHost(&hpos2, 2 * m * 8);
+        report("memcpy gather into alternating pinned buffers + touch kernel + sync", [&](int i) {
+            double *h = (i & 1) ? hpos2 : hpos;
+            memcpy(h, src.data(), 2 * m * 8);
+            k_touch<<<(m + 127) / 128, 128, 0, st>>>(h, hout, m, counter, nullptr, 0);
+            cudaStreamSynchronize(st);
+        });
+    }
     report("memcpy 160 KB pageable -> ordinary memory", [&](int) {
         static std::vector<double> d2(2 * 10000);
         memcpy(d2.data(), src.data(), 2 * m * 8);
