@@ -533,18 +533,21 @@ def c2_block(gc, workloads, torch, timed_calls_factory, world):
         out["note"] = ("%d ranks x (24 MB in + 8 MB out) per %.2f ms of kernel = %.0f GB/s of host DRAM traffic wanted from ONE host: "
                        "this weak block is bound by the host's memory system, not by the GPUs (profiles/scaling_r2.md)"
                        % (world, kernel_ms, world * 32e6 / (kernel_ms * 1e-3) / 1e9))
-    if world == 1:
-        # default API on this gridded input (exact grid detection on): the structured-grid GEMM path
-        gc.set_grid_detection(True)
-        for i in range(5):
-            gc.summate(k, z1, z2, pages[i % 2])
-        gp = gc.last_stats()["grid_path"]
-        t0 = time.perf_counter()
-        for i in range(50):
-            gc.summate(k, z1, z2, pages[i % 2])
-        out["default_api_grid_path"] = {"ms_per_step": (time.perf_counter() - t0) * 1e3 / 50, "grid_path": gp,
-                                        "note": "gstools_core.summate(pageable pos), detection on"}
-        gc.set_grid_detection(False)
+    # default API on this gridded input (exact grid detection on): the structured-grid GEMM path,
+    # which never moves the positions to the GPU (every rank at once when world > 1)
+    gc.set_grid_detection(True)
+    r = None
+    for i in range(5):
+        r = gc.summate(k, z1, z2, pages[i % 2])
+    gp = gc.last_stats()["grid_path"]
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(50):
+        r = gc.summate(k, z1, z2, pages[i % 2])
+    grid_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / 50
+    out["default_api_grid_path"] = {"ms_per_step": grid_ms, "value": world * pm / (grid_ms * 1e-3) / 1e9, "unit": UNIT,
+                                    "grid_path": gp, "note": "gstools_core.summate(pageable pos), detection on"}
+    gc.set_grid_detection(False)
     return out
 
 

@@ -476,3 +476,20 @@ def test_auto_pin_of_repeated_position_arrays():
         gc.set_auto_pin(0)
     d = gc.summate(k, z1, z2, pos)
     assert gc.last_stats()["pos_memory"] == 0 and np.array_equal(c, d)
+
+
+@pytest.mark.parametrize("m", [3000, 250_000])            # one-launch small path / chunk pipeline
+def test_reversed_position_views(m):
+    """ArrayView strides may be negative (numpy [::-1] views, src/lib.rs:43-46 binds whatever numpy passes)."""
+    k, z1, z2, pos = _rand(91, 3, 120, m)
+    ref = oracle.summate(k, z1, z2, pos, oracle.max_threads())
+    rev_pts = pos[:, ::-1]                                  # points in reverse order: pos_s1 < 0
+    assert rel_err(gc.summate(k, z1, z2, rev_pts), ref[::-1]) <= TOL
+    rev_dim = pos[::-1]                                     # coordinates swapped: pos_s0 < 0
+    ref_d = oracle.summate(k, z1, z2, np.ascontiguousarray(rev_dim), oracle.max_threads())
+    assert rel_err(gc.summate(k, z1, z2, rev_dim), ref_d) <= TOL
+    refi = oracle.summate_incompr(k, z1, z2, pos, oracle.max_threads())
+    assert rel_err(gc.summate_incompr(k, z1, z2, rev_pts), refi[:, ::-1]) <= TOL
+    every_other = pos[:, ::-2]
+    ref_e = oracle.summate(k, z1, z2, np.ascontiguousarray(every_other), oracle.max_threads())
+    assert rel_err(gc.summate(k, z1, z2, every_other), ref_e) <= TOL

@@ -24,9 +24,13 @@ def _runtime(name):
 
 
 def test_host_logic_under_asan_ubsan():
-    if not os.path.exists(ASAN_LIB):
+    sources = glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cuh")) + \
+        glob.glob(os.path.join(CSRC, "*.inc")) + glob.glob(os.path.join(CSRC, "*.cpp")) + [os.path.join(ROOT, "include", "gsfield.h")]
+    stale = os.path.exists(ASAN_LIB) and os.path.getmtime(ASAN_LIB) < max(os.path.getmtime(f) for f in sources)
+    if not os.path.exists(ASAN_LIB) or stale:
         if os.environ.get("GSF_BUILD_ASAN") != "1":
-            pytest.skip("libgsfield_asan.so not built (make -C gstools-core_b200/csrc asan, or GSF_BUILD_ASAN=1)")
+            pytest.skip("libgsfield_asan.so %s (make -C gstools-core_b200/csrc asan, or GSF_BUILD_ASAN=1)"
+                        % ("is older than the sources" if stale else "not built"))
         subprocess.run(["make", "-C", CSRC, "asan"], check=True)
     asan, ubsan = _runtime("libasan"), _runtime("libubsan")
     if not asan or not ubsan:
