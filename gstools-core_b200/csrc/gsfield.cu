@@ -828,7 +828,9 @@ std::vector<int64_t> chunk_schedule(int64_t m, bool single_launch, int64_t force
                       growth((int)env("GSF_CHUNK_GROWTH", 2)), cap_div((int)env("GSF_CHUNK_CAP_DIV", 6)),
                       down_max((int)env("GSF_CHUNK_DOWN", 64)) {}
         } kn;
-        const int64_t lo = std::max<int64_t>(1024, kn.lo / 1024 * 1024);
+        // first chunk: a quarter of a mid-sized problem, so that its kernel starts after a short copy
+        // (tools/e2e_size_sweep.py: 188 -> 164 us at 6e4 points x 1000 modes), never more than kn.lo
+        const int64_t lo = std::max<int64_t>(1024, (m <= kn.lo ? kn.lo : std::min<int64_t>(kn.lo, std::max<int64_t>(8192, m / 4))) / 1024 * 1024);
         const int growth = std::max(2, kn.growth);
         int64_t cap = std::min<int64_t>(kn.cap_abs, std::max<int64_t>(1 << 16, m / std::max(1, kn.cap_div)));
         cap = cap / 1024 * 1024;
@@ -1348,7 +1350,9 @@ int run_host_call(Problem p, const GridSpec *grid)
     // ---- structured grid?  explicit request, or exact auto-detection on host-resident positions
     GridSpec detected;
     const GridSpec *gs = grid;
-    const int threads1 = staging_threads(p.threads_hint, 1);
+    // (staged bytes per point: positions always; the result only when it cannot be copied out directly)
+    const int staged_bpp = 8 * p.dim + (out_kind == 0 ? 8 * p.nc() : 0);
+    const int threads1 = staging_threads(p.threads_hint, 1, p.N, staged_bpp);
     // Worth it only when the general kernel would take longer than the grid path's fixed cost
     // (~5 extra launches, tools/latency_sweep.py: break-even near 2e7 point*modes) and when the
     // per-axis tables stay small next to HBM.
@@ -1468,8 +1472,9 @@ int run_host_call(Problem p, const GridSpec *grid)
         // Small host-resident problems (one chunk anyway): stage the positions into the pinned
         // ring on the host and let the kernel read / write the pinned buffers in place -- saves the
         // explicit H2D and D2H copies and their launch latencies (tools/latency_sweep.py).
-        // (measured: wins up to ~400 KB of positions -- 51 vs 66 us at 1e4 points -- loses beyond)
-        const bool small_host = !zc && zero_copy && pos_kind != 2 && out_kind != 2 && (int64_t)p.dim * p.M * 8 <= 400 * 1024;
+        // (threshold swept with tools/e2e_size_sweep.py, GSF_SMALL_KB: the one-launch paths win up to ~800 KB of positions -- 60 vs 77 us at 2e4 points, 78 vs 97 us at 3e4 -- and lose beyond 1 MB)
+        static const int64_t small_bytes = []() { const char *e = getenv("GSF_SMALL_KB"); return (int64_t)(e && *e ? atoll(e) : 800) * 1024; }();
+        const bool small_host = !zc && zero_copy && pos_kind != 2 && out_kind != 2 && (int64_t)p.dim * p.M * 8 <= small_bytes;
         int64_t fused_rows = small_host ? small_fused_rows(p) : 0;
         static const bool promote = []() { const char *e = getenv("GSF_SMALL_PROMOTE"); return !(e && e[0] == '0'); }();
         if (fused_rows > 0 && promote && small_modes_repeat(*used[0], p)) fused_rows = 0;
@@ -1511,7 +1516,7 @@ int run_host_call(Problem p, const GridSpec *grid)
     } else {
         std::vector<std::thread> th;
         std::vector<int> Ps(G), Ls(G);
-        const int threads_g = staging_threads(p.threads_hint, G);   // per device: issuing thread + its share of the crew
+        const int threads_g = staging_threads(p.threads_hint, G, p.N, staged_bpp);   // per device: issuing thread + its share of the crew
         for (int g = 0; g < G; ++g) {
             int64_t j0, j1;
             shard_bounds(p.M, G, g, &j0, &j1);

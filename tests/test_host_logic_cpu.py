@@ -30,8 +30,10 @@ def test_chunk_schedule_covers_all_points(m):
     if m >= 10**6:
         assert s[0] == 32768 and s[-1] == 32768          # small first / last chunk: short exposed copies
         assert s[:3] == [32768, 65536, 131072]             # ramp up by doubling
-    if m <= 65536:
+    if m <= 32768:
         assert s == [m]
+    if 32768 < m <= 131072:
+        assert len(s) == 3 and s[0] == s[-1] == max(8192, m // 4) // 1024 * 1024   # quarter-sized first / last chunk
 
 
 def test_forced_chunk_size():

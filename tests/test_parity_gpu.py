@@ -430,7 +430,7 @@ def test_mode_record_cache_invalidation():
     """Identical modes skip the upload/pre-pass (records cached on the device); any change of the
     mode arrays -- even in place, same pointers -- must be noticed."""
     gc.shutdown()                                             # drop any cached records
-    k, z1, z2, pos = _rand(71, 3, 200, 30000)                 # beyond the one-launch small path (tests/test_small_gpu.py)
+    k, z1, z2, pos = _rand(71, 3, 200, 60000)                 # beyond the one-launch small path (tests/test_small_gpu.py)
     a1 = gc.summate(k, z1, z2, pos)
     n1 = gc.last_stats()["kernel_launches"]
     a2 = gc.summate(k, z1, z2, pos)

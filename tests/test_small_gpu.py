@@ -59,9 +59,9 @@ def _check(kind, d, n, m, seed=0, pos=None):
 
 @pytest.mark.parametrize("kind,d", [("summate", 1), ("summate", 2), ("summate", 3), ("summate_incompr", 2),
                                     ("summate_incompr", 3), ("summate_fourier", 2), ("summate_fourier", 3)])
-@pytest.mark.parametrize("n,m", [(1, 1), (7, 130), (100, 10000), (256, 3001), (33, 16384)])
+@pytest.mark.parametrize("n,m", [(1, 1), (7, 130), (100, 10000), (256, 3001), (33, 16384), (150, 33000)])
 def test_small_path_matches_oracle_and_general_kernel(kind, d, n, m):
-    if d * m * 8 > 400 * 1024:
+    if d * m * 8 > 800 * 1024:
         pytest.skip("beyond the small-path size")
     _check(kind, d, n, m, seed=n + m)
 
