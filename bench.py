@@ -414,7 +414,8 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": config_for(args, m_total),
         "e2e": {"value": pm_total / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_ms, "steps": Ke,
-                "h2d_bytes_per_step": st["h2d_bytes"], "d2h_bytes_per_step": st["d2h_bytes"],
+                "h2d_bytes_per_step": st["h2d_bytes"] * world, "d2h_bytes_per_step": st["d2h_bytes"] * world,
+                "h2d_bytes_per_step_per_rank": st["h2d_bytes"], "d2h_bytes_per_step_per_rank": st["d2h_bytes"],
                 "api": "gstools_core.%s(plain pageable numpy arrays) -> host ndarray, one call per rank on its shard" % kind,
                 "chunks_per_step": st["n_chunks"], "staging_threads": st["staging_threads"], "checksum": checksum,
                 "repetitions_ms_per_step": reps,

@@ -32,6 +32,23 @@
  *   - There is NO CPU fallback: without a usable CUDA device every compute entry point returns
  *     GSF_ERR_NO_DEVICE.
  *   - Calls are serialised per process by an internal mutex; callable from any thread.
+ *
+ * Environment (read once per process; tuning and A/B switches, none changes a result beyond the
+ * documented 1e-9 sigma contract)
+ *   GSF_DEVICES="0,1,.."      default device list of the host-memory entry points (gsf_set_devices overrides)
+ *   GSF_GRID_DETECT=0         no automatic structured-grid detection (gsf_set_grid_detection)
+ *   GSF_POLY_DEGREE=6         always the high-degree cosine polynomial (gsf_set_poly_degree)
+ *   GSF_STAGING_THREADS=n     host threads staging pageable memory per device (default: from the demand)
+ *   GSF_NUMA_BIND=0|1         one process per GPU: bind the rank's threads to the GPU's NUMA node
+ *                             (default: only when a launcher exports LOCAL_WORLD_SIZE > 1)
+ *   GSF_ZERO_COPY=0           pinned pos/out through the copy pipeline instead of mapped access
+ *   GSF_SMALL_KB=n            positions up to n KB take the one-launch paths (default 800)
+ *   GSF_SMALL_FUSED=0, GSF_SMALL_PROMOTE=0   small calls: no gsf_small_kernel / no repeat-mode promotion
+ *   GSF_CHUNK_FIRST / _CAP / _CAP_DIV / _GROWTH / _DOWN, GSF_TAIL_WAVES, GSF_GRID_KSPLIT, GSF_GRID_CHUNK_MB
+ *                             pipeline chunk schedule, short-tile tail, grid-path split / chunk size
+ *   GSF_PINNED_CACHE_MB, GSF_PINNED_LIVE_MB   caching pinned allocator behind gsf_host_alloc
+ *   GSF_POOL_SPIN_US          how long idle pool workers spin before sleeping (0 under a multi-rank launcher)
+ *   GSF_TRACE=1               per-phase host timeline of every call on stderr
  */
 #ifndef GSFIELD_H
 #define GSFIELD_H
