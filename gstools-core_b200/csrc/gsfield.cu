@@ -1450,9 +1450,17 @@ int run_host_call(Problem p, const GridSpec *grid)
         // tiles (P = 1: ~5 MB in the first wave instead of ~12 MB) start the machine sooner unless
         // the per-point work is long (N >= 4000).  Measured on C2: 1.02 ms vs 1.06 ms for the
         // chunked copy pipeline (tools/e2e_probe.py).  GSF_ZERO_COPY=0 restores the pipeline.
+        // Several ranks on one host (one process per GPU): the copy-engine pipeline moves the same bytes
+        // with fewer, larger requests than SM-issued mapped loads -- 1.45 vs 1.59 ms per C2 call with
+        // eight ranks saturating the host's memory system (profiles/c2_weak_r2.md) -- so mapped access of
+        // LARGE pinned arrays is the single-rank default only.  (Small calls keep their mapped buffers.)
         static const int zero_copy = []() { const char *e = getenv("GSF_ZERO_COPY"); return e && *e ? atoi(e) : 1; }();
+        static const bool zero_copy_large = []() {
+            const char *e = getenv("GSF_ZERO_COPY");
+            return e && *e ? atoi(e) != 0 : local_world_size() <= 1;
+        }();
         bool zc = false;
-        if (zero_copy && pos_kind == 1 && out_kind == 1 && p.ps1 == 1) {
+        if (zero_copy_large && pos_kind == 1 && out_kind == 1 && p.ps1 == 1) {
             void *dpos = nullptr, *dout = nullptr;
             cudaSetDevice(used[0]->dev);
             if (cudaHostGetDevicePointer(&dpos, const_cast<double *>(p.pos), 0) == cudaSuccess &&
