@@ -925,7 +925,8 @@ int run_shard(DeviceCtx &d, const Problem &p, int64_t j_beg, int64_t j_end, int 
         sg->stage_in = stage_in;
         sg->stage_out = stage_out;
         sg->plan(sizes, j_beg);
-        const int depth = (int)std::min<int64_t>(n_chunks, n_chunks <= kSlots ? kSlots : 5);
+        static const int ring_depth = []() { const char *e = getenv("GSF_RING_DEPTH"); return e && *e ? std::max(kSlots, std::min(kMaxRing, atoi(e))) : 5; }();
+        const int depth = (int)std::min<int64_t>(n_chunks, n_chunks <= kSlots ? kSlots : ring_depth);
         if (stage_in) {
             sg->ring_in = depth;
             sg->slot_in = (size_t)p.dim * chunk;

@@ -33,6 +33,8 @@ if rank == 0:
     print("world=%d GSF_ZERO_COPY=%s GSF_STAGING_THREADS=%s GSF_PAGEABLE_DIRECT=%s" % (world, os.environ.get("GSF_ZERO_COPY", "-"),
           os.environ.get("GSF_STAGING_THREADS", "-"), os.environ.get("GSF_PAGEABLE_DIRECT", "-")), flush=True)
 run("pageable")
+if len(sys.argv) > 1 and sys.argv[1] == "pageable":
+    dist.destroy_process_group(); sys.exit(0)
 h = [gc.pinned(p) for p in pages]
 run("caller-pinned")
 for x in h: x.release()
