@@ -63,6 +63,11 @@ struct GridTableArgs {
     int bnp;                    // grid_bnp(NT)
     int n_col_blocks;
     double scale;
+    // Mode groups (tensor-structured modes, e.g. the Fourier method's lattice k = (kx_a, ky_b)): `mode_group`
+    // consecutive modes share every wave-vector component except the last, so their F rows can be
+    // summed BEFORE the GEMM:  sum_i Re(G_i F_i) = sum_i' Re(G_i' sum_il F_(i',il)).  n_modes then counts
+    // the groups (the GEMM's contraction shrinks by the group size); 1 = every mode on its own.
+    int mode_group;
 };
 
 __global__ void gsf_grid_tables(GridTableArgs a)
@@ -72,7 +77,37 @@ __global__ void gsf_grid_tables(GridTableArgs a)
     if (i >= a.n_modes_pad) return;
     const bool last = ax == a.dim - 1;
     const bool live = i < a.n_modes;
-    const double *rec = a.rec + (live ? i : 0) * a.rec_doubles;
+    const int group = a.mode_group;
+    const double *rec = a.rec + (live ? i * group : 0) * a.rec_doubles;   // first mode of the group
+    if (last && group > 1) {
+        // F row of a mode group = sum of its members' F rows (each with its own last wave number,
+        // phase and amplitude), accumulated in member order
+        for (int64_t j = blockIdx.y; j < a.axis_n[ax]; j += gridDim.y) {
+            double re[3] = {0.0, 0.0, 0.0}, im[3] = {0.0, 0.0, 0.0};
+            if (live) {
+                const double x = a.axis[ax][j * a.axis_s[ax]];
+                for (int il = 0; il < group; ++il) {
+                    const double *r = rec + (int64_t)il * a.rec_doubles;
+                    double c, s;
+                    sincospi(fma(r[ax], x, r[a.dim]), &s, &c);
+                    for (int comp = 0; comp < a.nc; ++comp) {
+                        const double amp = __dmul_rn(r[a.dim + 1 + comp], a.scale);
+                        re[comp] = fma(amp, c, re[comp]);
+                        im[comp] = fma(amp, s, im[comp]);
+                    }
+                }
+            }
+            for (int comp = 0; comp < a.nc; ++comp) {
+                const int64_t col = j * a.nc + comp;
+                const int64_t blk = col / a.cols_per_block;
+                const int64_t cin = col - blk * a.cols_per_block;
+                double *base = a.F + (blk * (2 * a.n_modes_pad) + 2 * i) * a.bnp + cin;
+                base[0] = re[comp];
+                base[a.bnp] = -im[comp];
+            }
+        }
+        return;
+    }
     for (int64_t j = blockIdx.y; j < a.axis_n[ax]; j += gridDim.y) {   // axis index
         double c = 0.0, s = 0.0;
         if (live) {

@@ -386,6 +386,7 @@ struct Problem {
     double offset[3] = {0.0, 0.0, 0.0};
     // memory kind of the mode arrays (classify): filled once per call by run_host_call, -1 = not yet known
     int mem_k = -1, mem_k_dev = -1, mem_z1 = -1, mem_z2 = -1, mem_sf = -1;
+    int64_t mode_group = 1;              // structured-grid path: consecutive modes sharing all but the last wave-vector component
     int nc() const { return kind == gsf::kIncompr ? dim : 1; }
     int rec() const { return gsf::rec_doubles(dim, nc()); }
 };
@@ -1217,6 +1218,7 @@ void collect_stats(const Problem &p, const std::vector<DeviceCtx *> &used, doubl
     s.poly_degree = grid_path ? 0 : (p.dim > gsf::kMaxTemplateDim ? gsf::kHiDeg : p.deg);
     s.fp64_slots = grid_path ? 0 : p.dim + gsf::cos_slots(s.poly_degree) + p.nc();
     s.n_devices = (int)used.size();
+    s.mode_group = grid_path ? (int32_t)std::min<int64_t>(p.mode_group, 0x7fffffff) : 0;
     c.last_devs.clear();
     for (DeviceCtx *d : used) {
         s.h2d_bytes += d->h2d_bytes;
@@ -1408,6 +1410,7 @@ int run_host_call(Problem p, const GridSpec *grid)
 
     int P = 0, L = 0;
     if (gs) {
+        p.mode_group = detect_mode_group(p);   // tensor-structured modes shrink the GEMM's contraction
         const int64_t R = gs->rows();
         if (G == 1) {
             rc = run_grid(*used[0], p, *gs, 0, R, out_kind, threads1, axes_on_device, cancel);

@@ -46,7 +46,7 @@ class GsfStats(ctypes.Structure):
         ("points_per_thread", ctypes.c_int32), ("lanes_per_point", ctypes.c_int32),
         ("pos_memory", ctypes.c_int32), ("out_memory", ctypes.c_int32), ("grid_path", ctypes.c_int32),
         ("poly_degree", ctypes.c_int32), ("fp64_slots", ctypes.c_int32), ("staging_threads", ctypes.c_int32),
-        ("reserved", ctypes.c_int32),
+        ("mode_group", ctypes.c_int32),
     ]
 
     def as_dict(self):

@@ -96,7 +96,7 @@ typedef struct gsf_stats {
     int32_t poly_degree;    /* degree of the cosine polynomial the summation kernel used (0: grid path)  */
     int32_t fp64_slots;     /* FP64-pipe instructions per point*mode of that kernel: dim + 5 + degree + nc */
     int32_t staging_threads;/* host threads that staged pageable memory through the pinned rings         */
-    int32_t reserved;
+    int32_t mode_group;     /* grid path: consecutive modes summed before the GEMM (tensor-structured modes), 1 = none; 0 otherwise */
 } gsf_stats;
 
 /* ---- the three reference functions ------------------------------------------------------- */

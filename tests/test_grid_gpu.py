@@ -265,3 +265,64 @@ def test_mode_split_launches_are_exact_and_deterministic(shape, n):
     gc.summate_grid(k, z1, z2, axes, out=out)
     torch.cuda.synchronize()
     assert rel_err(out.cpu().numpy(), ref) <= TOL
+
+
+def _lattice_modes(shape, seed):
+    """wave vectors on a tensor lattice, flattened in C order (last component fastest) -- what the Fourier
+    generator passes: modes = meshgrid(kx, ky[, kz], indexing='ij').reshape(dim, -1)"""
+    rng = np.random.default_rng(seed)
+    axes_k = [np.sort(rng.uniform(-2.0, 2.0, s)) for s in shape]
+    k = np.ascontiguousarray(np.stack([g.ravel() for g in np.meshgrid(*axes_k, indexing="ij")]))
+    n = k.shape[1]
+    return k, rng.normal(size=n), rng.normal(size=n), rng.uniform(0.1, 1.0, size=n)
+
+
+@pytest.mark.parametrize("kshape,pshape", [((12, 16), (70, 90)), ((5, 4, 8), (9, 10, 40)), ((3, 100), (33, 64))])
+def test_tensor_structured_modes_are_summed_per_group(kshape, pshape):
+    """Modes on a lattice (Fourier method): runs of modes sharing all but the last wave-vector component
+    are summed in the F table and the GEMM contracts over the runs only.  Same field as the general
+    kernel / the oracle; anything that breaks the structure falls back to one row per mode."""
+    d = len(kshape)
+    k, z1, z2, sf = _lattice_modes(kshape, 41)
+    axes = [np.linspace(0.0, 25.0, s, endpoint=False) for s in pshape]
+    pos = expand(axes)
+    group = kshape[-1]
+    ref = oracle.summate_fourier(sf, k, z1, z2, pos, oracle.max_threads())
+    got = gc.summate_fourier_grid(sf, k, z1, z2, axes)
+    st = gc.last_stats()
+    assert st["grid_path"] == 2 and st["mode_group"] == group, st
+    assert rel_err(got, ref) <= TOL
+    assert np.array_equal(got, gc.summate_fourier_grid(sf, k, z1, z2, axes))
+    gc.set_grid_detection(False)
+    gen = gc.summate_fourier(sf, k, z1, z2, pos)                      # general point x mode kernel
+    gc.set_grid_detection(None)
+    assert rel_err(got, gen) <= TOL
+    # scalar and incompressible calls see the same structure
+    assert rel_err(gc.summate_grid(k, z1, z2, axes), oracle.summate(k, z1, z2, pos, oracle.max_threads())) <= TOL
+    assert gc.last_stats()["mode_group"] == group
+    goti = gc.summate_incompr_grid(k, z1, z2, axes)
+    assert gc.last_stats()["mode_group"] == group
+    refi = oracle.summate_incompr(k, z1, z2, pos, oracle.max_threads())
+    ok = np.isfinite(refi)                                             # (a zero wave vector gives NaN, as in the reference)
+    assert np.array_equal(ok, np.isfinite(goti)) and rel_err(goti[ok], refi[ok]) <= TOL
+    # one perturbed component breaks the lattice: every mode on its own again, same answer
+    k2 = k.copy(); k2[0, group + 1] += 1e-3
+    got2 = gc.summate_fourier_grid(sf, k2, z1, z2, axes)
+    assert gc.last_stats()["mode_group"] == 1
+    assert rel_err(got2, oracle.summate_fourier(sf, k2, z1, z2, pos, oracle.max_threads())) <= TOL
+    # lattice flattened with the FIRST component fastest: no runs, plain path
+    k3 = np.ascontiguousarray(np.stack([g.ravel(order="F") for g in np.meshgrid(*[np.unique(k[a]) for a in range(d)], indexing="ij")]))
+    got3 = gc.summate_fourier_grid(sf, k3, z1, z2, axes)
+    assert gc.last_stats()["mode_group"] == 1
+    assert rel_err(got3, oracle.summate_fourier(sf, k3, z1, z2, pos, oracle.max_threads())) <= TOL
+
+
+def test_c4_fourier_lattice_through_the_default_api():
+    """BASELINE configs[3] scaled down: the plain reference-shaped call detects the grid in `pos` AND the
+    lattice in `modes` (100 x 100 wave vectors -> 100 groups of 100)."""
+    w = workloads.make("c4", 1.0 / 256)
+    got = gc.summate_fourier(*w["args"])
+    st = gc.last_stats()
+    assert st["grid_path"] == 1 and st["mode_group"] == 100, st
+    ref = oracle.summate_fourier(*w["args"], oracle.max_threads())
+    assert rel_err(got, ref) <= TOL
