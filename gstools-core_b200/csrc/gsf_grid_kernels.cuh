@@ -79,35 +79,7 @@ __global__ void gsf_grid_tables(GridTableArgs a)
     const bool live = i < a.n_modes;
     const int group = a.mode_group;
     const double *rec = a.rec + (live ? i * group : 0) * a.rec_doubles;   // first mode of the group
-    if (last && group > 1) {
-        // F row of a mode group = sum of its members' F rows (each with its own last wave number,
-        // phase and amplitude), accumulated in member order
-        for (int64_t j = blockIdx.y; j < a.axis_n[ax]; j += gridDim.y) {
-            double re[3] = {0.0, 0.0, 0.0}, im[3] = {0.0, 0.0, 0.0};
-            if (live) {
-                const double x = a.axis[ax][j * a.axis_s[ax]];
-                for (int il = 0; il < group; ++il) {
-                    const double *r = rec + (int64_t)il * a.rec_doubles;
-                    double c, s;
-                    sincospi(fma(r[ax], x, r[a.dim]), &s, &c);
-                    for (int comp = 0; comp < a.nc; ++comp) {
-                        const double amp = __dmul_rn(r[a.dim + 1 + comp], a.scale);
-                        re[comp] = fma(amp, c, re[comp]);
-                        im[comp] = fma(amp, s, im[comp]);
-                    }
-                }
-            }
-            for (int comp = 0; comp < a.nc; ++comp) {
-                const int64_t col = j * a.nc + comp;
-                const int64_t blk = col / a.cols_per_block;
-                const int64_t cin = col - blk * a.cols_per_block;
-                double *base = a.F + (blk * (2 * a.n_modes_pad) + 2 * i) * a.bnp + cin;
-                base[0] = re[comp];
-                base[a.bnp] = -im[comp];
-            }
-        }
-        return;
-    }
+    if (last && group > 1) return;   // the F rows of mode groups come from gsf_grid_group_rows
     for (int64_t j = blockIdx.y; j < a.axis_n[ax]; j += gridDim.y) {   // axis index
         double c = 0.0, s = 0.0;
         if (live) {
@@ -128,6 +100,44 @@ __global__ void gsf_grid_tables(GridTableArgs a)
             double *base = a.F + (blk * (2 * a.n_modes_pad) + 2 * i) * a.bnp + cin;
             base[0] = __dmul_rn(amp, c);
             base[a.bnp] = -__dmul_rn(amp, s);
+        }
+    }
+}
+
+// F rows of mode groups (GridTableArgs::mode_group > 1): row i' = sum over the group's members of
+// A_il * exp(i*pi*(kh_last,il * x_j - th_il)), each member with its own last wave number, phase and
+// amplitude, accumulated in member order.  Thread = one point j of the last axis (coalesced writes of
+// the tiled F rows); all threads of a block walk the same group, so the member records are uniform
+// (broadcast) loads.  blockIdx.y strides over the groups.
+__global__ void __launch_bounds__(128) gsf_grid_group_rows(GridTableArgs a)
+{
+    const int ax = a.dim - 1;
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= a.axis_n[ax]) return;
+    const int group = a.mode_group;
+    const double x = a.axis[ax][j * a.axis_s[ax]];
+    for (int64_t i = blockIdx.y; i < a.n_modes_pad; i += gridDim.y) {
+        double re[3] = {0.0, 0.0, 0.0}, im[3] = {0.0, 0.0, 0.0};
+        if (i < a.n_modes) {
+            const double *rec = a.rec + i * group * a.rec_doubles;
+            for (int il = 0; il < group; ++il) {
+                const double *r = rec + (int64_t)il * a.rec_doubles;
+                double c, s;
+                sincospi(fma(__ldg(r + ax), x, __ldg(r + a.dim)), &s, &c);
+                for (int comp = 0; comp < a.nc; ++comp) {
+                    const double amp = __dmul_rn(__ldg(r + a.dim + 1 + comp), a.scale);
+                    re[comp] = fma(amp, c, re[comp]);
+                    im[comp] = fma(amp, s, im[comp]);
+                }
+            }
+        }
+        for (int comp = 0; comp < a.nc; ++comp) {
+            const int64_t col = j * a.nc + comp;
+            const int64_t blk = col / a.cols_per_block;
+            const int64_t cin = col - blk * a.cols_per_block;
+            double *base = a.F + (blk * (2 * a.n_modes_pad) + 2 * i) * a.bnp + cin;
+            base[0] = re[comp];
+            base[a.bnp] = -im[comp];
         }
     }
 }
