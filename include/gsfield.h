@@ -37,6 +37,7 @@
  * documented 1e-9 sigma contract)
  *   GSF_DEVICES="0,1,.."      default device list of the host-memory entry points (gsf_set_devices overrides)
  *   GSF_GRID_DETECT=0         no automatic structured-grid detection (gsf_set_grid_detection)
+ *   GSF_MODE_GROUPS=0         structured-grid path: never sum runs of tensor-structured modes before the GEMM
  *   GSF_POLY_DEGREE=6         always the high-degree cosine polynomial (gsf_set_poly_degree)
  *   GSF_STAGING_THREADS=n     host threads staging pageable memory per device (default: from the demand)
  *   GSF_NUMA_BIND=0|1         one process per GPU: bind the rank's threads to the GPU's NUMA node
@@ -137,6 +138,10 @@ int gsf_summate_fourier(int dim, int64_t n_modes, int64_t n_points,
  *   factorises per axis and runs as an FP64 tensor-core GEMM (2 FMA per point*mode instead of 15).
  * The plain entry points detect such grids in host-resident `pos` automatically (exact, bitwise
  * check; gsf_set_grid_detection(0) or GSF_GRID_DETECT=0 turns that off).
+ * On this path tensor-structured MODES are exploited too: when consecutive runs of g host-resident modes
+ * share every wave-vector component but the last (the Fourier method's lattice, modes = meshgrid(kx, ky
+ * [, kz]) flattened in C order; detected exactly), the runs are summed before the GEMM and the
+ * contraction shrinks by g (gsf_stats::mode_group; GSF_MODE_GROUPS=0 turns it off).
  * Set struct_size = sizeof(gsf_request); zero-initialise the rest you do not use (scale = 1). */
 typedef struct gsf_request {
     int32_t struct_size;
