@@ -263,10 +263,15 @@ struct SumArgs {
 // hits, and that is worth several percent on an FP64-bound loop.
 //   style 0: one point after the other; style 1: all P points in lockstep, step by step.
 #ifndef GSF_TUNE_STYLE
+// (re-measured with the degree-5 polynomial, profiles/tune_sum_r2_deg5.txt: unroll 16 is worth
+//  +0.6 .. 1.5 % on the 2-D / 3-D kernels, the 2-D scalar P = 3 kernel keeps 4, 1-D prefers style 0)
 template <int D, int NC, int P>
-__host__ __device__ constexpr int gsf_style() { return 1; }
+__host__ __device__ constexpr int gsf_style() { return D == 1 ? 0 : 1; }
 template <int D, int NC, int P>
-__host__ __device__ constexpr int gsf_unroll() { return (D == 2 && NC == 1 && P == 3) ? 4 : 8; }   // re-measured with the monic polynomial
+__host__ __device__ constexpr int gsf_unroll()
+{
+    return (D == 2 && NC == 1 && P == 3) ? 4 : ((D == 1 || D > 3 || (NC == 3 && P == 4) || (D == 2 && NC == 1 && P == 1)) ? 8 : 16);
+}
 #else
 template <int D, int NC, int P>
 __host__ __device__ constexpr int gsf_style() { return GSF_TUNE_STYLE; }

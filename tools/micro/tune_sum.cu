@@ -27,9 +27,9 @@ double run(int64_t m, int n_modes, double tail_waves)
     SumArgs a{};
     a.rec = drec; a.n_modes = n_modes; a.pos = dpos; a.ps0 = m; a.ps1 = 1; a.n_points = m;
     a.out = dout; a.os0 = 1; a.os1 = NC;
-    gsf::poly_constants(a.coef);
+    gsf::poly_constants(gsf::kFastDeg, a.coef);
     const int64_t tile = (int64_t)P * kThreads;
-    int64_t tail_pts = (int64_t)(tail_waves * 148 * 8 * (double)tile);
+    int64_t tail_pts = (int64_t)(tail_waves * 148 * 8 * (double)tile);   // as launch_sum
     if (tail_pts > m) tail_pts = m;
     int64_t n_big = P > 1 ? (m - tail_pts) / tile : (m + tile - 1) / tile;
     int64_t n_small = P > 1 ? (m - n_big * tile + kThreads - 1) / kThreads : 0;
@@ -38,7 +38,7 @@ double run(int64_t m, int n_modes, double tail_waves)
     float best = 1e9f;
     for (int it = 0; it < 6; ++it) {
         cudaEventRecord(e0);
-        gsf_sum_kernel<D, NC, P, 1><<<(unsigned)(n_big + n_small), kThreads>>>(a);
+        gsf_sum_kernel<D, NC, P, 1, gsf::kFastDeg><<<(unsigned)(n_big + n_small), kThreads>>>(a);
         cudaEventRecord(e1); cudaEventSynchronize(e1);
         float ms; cudaEventElapsedTime(&ms, e0, e1);
         if (it >= 1 && ms < best) best = ms;
@@ -49,7 +49,7 @@ double run(int64_t m, int n_modes, double tail_waves)
 
 int main()
 {
-    printf("monic=%d style=%d unroll=%d |", GSF_POLY_MONIC, GSF_TUNE_STYLE, GSF_TUNE_UNROLL);
+    printf("deg=%d style=%d unroll=%d |", gsf::kFastDeg, GSF_TUNE_STYLE, GSF_TUNE_UNROLL);
     printf(" d3s P3 1M %.0f 4M %.0f |", run<3, 1, 3>(1000000, 1000, 0.5), run<3, 1, 3>(4000000, 1000, 0.5));
     printf(" d3s P4 4M %.0f | d3s P2 4M %.0f |", run<3, 1, 4>(4000000, 1000, 0.5), run<3, 1, 2>(4000000, 1000, 0.5));
     printf(" d3i P3 1M %.0f 4M %.0f | d3i P2 4M %.0f |", run<3, 3, 3>(1000000, 1000, 0.5), run<3, 3, 3>(4000000, 1000, 0.5), run<3, 3, 2>(4000000, 1000, 0.5));
