@@ -1754,6 +1754,15 @@ int gsf_debug_chunk_schedule(int64_t n_points, int64_t forced_chunk, int64_t *si
     return (int)v.size() > max_sizes ? -(int)v.size() : n;
 }
 
+int64_t gsf_debug_mode_group(int dim, int64_t n_modes, const double *modes, int64_t modes_s0, int64_t modes_s1)
+{
+    if (!modes || dim < 1 || n_modes < 0) return 1;
+    Problem p{};
+    p.dim = dim; p.N = n_modes; p.k = modes; p.ks0 = modes_s0; p.ks1 = modes_s1;
+    p.mem_k = 0;   // host-resident by contract of this entry point
+    return detect_mode_group(p);
+}
+
 int gsf_debug_parse_cpulist(const char *list, int *cpus, int max_cpus)
 {
     if (!list || (max_cpus > 0 && !cpus)) return fail(GSF_ERR_ARG, "bad arguments");

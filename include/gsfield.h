@@ -219,6 +219,10 @@ int gsf_debug_chunk_schedule(int64_t n_points, int64_t forced_chunk, int64_t *si
 /* The sysfs cpulist parser behind the rank-to-NUMA-node binding ("0-15,64-79"): writes up to max_cpus
  * cpu ids in increasing order, returns how many the list names. */
 int gsf_debug_parse_cpulist(const char *list, int *cpus, int max_cpus);
+/* The exact detector of tensor-structured (lattice) modes used by the structured-grid path: returns the
+ * common run length g of consecutive host-resident modes sharing all but the last wave-vector component,
+ * or 1 when there is no such structure. */
+int64_t gsf_debug_mode_group(int dim, int64_t n_modes, const double *modes, int64_t modes_s0, int64_t modes_s1);
 int gsf_debug_detect_grid(int dim, int64_t n_points, const double *pos, int64_t pos_s0, int64_t pos_s1,
                           int64_t *axis_n);
 

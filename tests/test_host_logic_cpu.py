@@ -136,3 +136,35 @@ def test_cpulist_parser_of_the_numa_binding():
     assert parse("2-2,2") == [2]
     assert parse("") == [] and parse("\n") == []
     assert parse("0-1,x") == [0, 1]
+
+
+def test_mode_group_detector():
+    """detect_mode_group (structured-grid path): run length of consecutive modes sharing all but the last
+    wave-vector component -- exact, and 1 whenever the structure is not perfect."""
+    L.gsf_debug_mode_group.argtypes = [ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64]
+    L.gsf_debug_mode_group.restype = ctypes.c_int64
+
+    def group(k):
+        return L.gsf_debug_mode_group(k.shape[0], k.shape[1], k.ctypes.data, k.strides[0] // 8, k.strides[1] // 8)
+
+    def lattice(shape, order="C"):
+        axes = [np.linspace(0.1, 3.0, s) * (a + 1) for a, s in enumerate(shape)]
+        return np.ascontiguousarray(np.stack([g.ravel(order=order) for g in np.meshgrid(*axes, indexing="ij")]))
+
+    assert group(lattice((12, 16))) == 16                      # Fourier lattice, last component fastest
+    assert group(lattice((5, 4, 8))) == 8
+    assert group(lattice((100, 100))) == 100                   # C4
+    assert group(lattice((12, 16), order="F")) == 1            # first component fastest: no runs
+    assert group(np.random.default_rng(0).normal(size=(3, 1000))) == 1      # randomization method
+    k = lattice((12, 16)); k[0, 17] += 1e-12
+    assert group(k) == 1                                       # one perturbed component
+    k = lattice((12, 16))[:, :-16]; k = np.ascontiguousarray(np.concatenate([k, k[:, :8]], axis=1))
+    assert group(k) == 1                                       # last run shorter than the others
+    assert group(lattice((4, 8))) == 1                         # fewer than 64 modes: not worth it
+    assert group(lattice((40, 2))) == 1                        # runs shorter than 4
+    k = lattice((12, 16))
+    assert group(k[:, ::-1]) == 16                             # negative mode stride (a view)
+    two = np.ascontiguousarray(np.concatenate([lattice((6, 16)), lattice((6, 16))], axis=1))
+    assert group(two) == 16                                    # repeated outer values in separate runs are fine
+    merged = np.ascontiguousarray(np.concatenate([lattice((1, 16)), lattice((1, 16)), lattice((10, 16))[:, 16:]], axis=1))
+    assert group(merged) == 1                                  # one run twice as long as the rest
