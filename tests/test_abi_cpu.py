@@ -207,3 +207,65 @@ def test_native_binding_fast_lane_and_its_fallbacks():
         gc.summate(k.astype(np.float32), z1, z2, pos)
     with pytest.raises(ValueError):
         gc.summate(k, z1[:5], z2, pos)
+
+
+def test_native_binding_marshalling_against_recording_callbacks():
+    """The native binding with the three C entry points replaced by ctypes callbacks that record what they
+    were given: dimensions, ELEMENT strides of arbitrary views (incl. negative), the (d, M) Fortran-ordered
+    result of summate_incompr, num_threads, and status propagation -- no GPU involved."""
+    from gstools_core import _gsf_native as nat
+    i64, vp, ci = ctypes.c_int64, ctypes.c_void_p, ctypes.c_int
+    D = ctypes.POINTER(ctypes.c_double)
+    seen = {}
+
+    def read(ptr, n, stride):
+        return [ptr[i * stride] for i in range(n)]
+
+    @ctypes.CFUNCTYPE(ci, ci, i64, i64, D, i64, i64, D, i64, D, i64, D, i64, i64, D, ci)
+    def fake_summate(d, n, m, k, ks0, ks1, z1, z1s, z2, z2s, pos, ps0, ps1, out, nt):
+        seen.update(kind=0, d=d, n=n, m=m, ks=(ks0, ks1), zs=(z1s, z2s), ps=(ps0, ps1), nt=nt,
+                    k00=k[0], k_row1=read(k, n, ks1)[:3] if d > 0 else None, z1=read(z1, n, z1s), pos_last=pos[(d - 1) * ps0 + (m - 1) * ps1])
+        for j in range(m):
+            out[j] = 100.0 + j
+        return seen.get("rc", 0)
+
+    @ctypes.CFUNCTYPE(ci, ci, i64, i64, D, i64, i64, D, i64, D, i64, D, i64, i64, D, i64, i64, ci)
+    def fake_incompr(d, n, m, k, ks0, ks1, z1, z1s, z2, z2s, pos, ps0, ps1, out, os0, os1, nt):
+        seen.update(kind=1, d=d, n=n, m=m, os=(os0, os1), nt=nt)
+        for a in range(d):
+            for j in range(m):
+                out[a * os0 + j * os1] = 10.0 * a + j
+        return 0
+
+    @ctypes.CFUNCTYPE(ci, ci, i64, i64, D, i64, D, i64, i64, D, i64, D, i64, D, i64, i64, D, ci)
+    def fake_fourier(d, n, m, sf, sfs, k, ks0, ks1, z1, z1s, z2, z2s, pos, ps0, ps1, out, nt):
+        seen.update(kind=2, d=d, n=n, m=m, sf=read(sf, n, sfs), sfs=sfs)
+        for j in range(m):
+            out[j] = -1.0 * j
+        return 0
+
+    addr = lambda f: ctypes.cast(f, vp).value                      # noqa: E731
+    try:
+        nat.bind(addr(fake_summate), addr(fake_incompr), addr(fake_fourier), np.ndarray, np.empty, np.float64, 256 * 1024)
+        rng = np.random.default_rng(3)
+        kbig, zbig, pbig = rng.normal(size=(3, 14)), rng.normal(size=30), rng.normal(size=(3, 40))
+        k, z1, z2 = kbig[:, ::2], zbig[0:21:3], zbig[20::-3]        # views: strides 2, 3, -3 (7 modes)
+        pos = pbig[::-1, ::4]                                        # rows reversed, every 4th point (10 points)
+        out = nat.summate(k, z1, z2, pos, 5)
+        assert isinstance(out, np.ndarray) and out.shape == (10,) and np.array_equal(out, 100.0 + np.arange(10))
+        assert (seen["d"], seen["n"], seen["m"], seen["nt"]) == (3, 7, 10, 5)
+        assert seen["ks"] == (14, 2) and seen["zs"] == (3, -3) and seen["ps"] == (-40, 4)
+        assert seen["k00"] == k[0, 0] and seen["z1"] == list(z1) and seen["pos_last"] == pos[2, 9]
+        outi = nat.summate_incompr(k, z1, z2, pos, None)
+        assert outi.shape == (3, 10) and outi.flags.f_contiguous and seen["os"] == (1, 3) and seen["nt"] == 0
+        assert np.array_equal(outi, 10.0 * np.arange(3)[:, None] + np.arange(10)[None, :])     # src/field.rs:166-174 layout
+        sf = np.linspace(1, 2, 14)[::2]
+        outf = nat.summate_fourier(sf, k, z1, z2, pos, None)
+        assert seen["kind"] == 2 and seen["sf"] == list(sf) and seen["sfs"] == 2 and np.array_equal(outf, -1.0 * np.arange(10))
+        seen["rc"] = 3                                               # a non-zero status comes back as an int for the wrapper to raise
+        assert nat.summate(k, z1, z2, pos, None) == 3
+    finally:
+        seen.pop("rc", None)
+        gc._native = None
+        gc._bind_native(gc._load())                                  # restore the real entry points
+    assert gc._native is not None
