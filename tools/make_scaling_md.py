@@ -3,10 +3,10 @@
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 P = lambda f: os.path.join(ROOT, "profiles", f)
-r = {n: json.load(open(P(f))) for n, f in ((1, "bench_r2_c5_1gpu.json"), (2, "bench_r2_n2.json"), (8, "bench_r2_n8.json")) if os.path.exists(P(f))}
+r = {n: json.load(open(P(f))) for n, f in ((1, "bench_r2_c5_1gpu.json"), (2, "bench_r2_n2.json"), (4, "bench_r2_n4.json"), (8, "bench_r2_n8.json")) if os.path.exists(P(f))}
 L = ["# Strong scaling of the north-star sweep, round 2 (C5: 1e4 modes x 1e8 points, one process per GPU)", "",
      "The driver's command line for every N: `python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N --steps 20 --warmup 5`",
-     "(N = 1: `python bench.py --steps 20 --warmup 5`).  Full JSON lines: `profiles/bench_r2_c5_1gpu.json`, `bench_r2_n2.json`, `bench_r2_n8.json`.",
+     "(N = 1: `python bench.py --steps 20 --warmup 5`).  Full JSON lines: `profiles/bench_r2_c5_1gpu.json`, `bench_r2_n2.json`, `bench_r2_n4.json`, `bench_r2_n8.json` (N = 4 was run last, after the degree-5 schedule retune: +0.5 % per GPU; N = 1 on that tree: `bench_r2_c5_1gpu_retuned.json`).",
      "Hosts: 1-GPU box 16 vCPUs, 2-GPU box 24 vCPUs, 8-GPU box 32 vCPUs / ONE NUMA node / 1 TB RAM / NV18 all-to-all.", "",
      "| N | value G pm/s (device-timed) | x N=1 | ms/step | e2e G pm/s (pageable host arrays) | x N=1 | e2e ms/step | roofline frac (kernel vs DFMA peak) |",
      "|---|---|---|---|---|---|---|---|"]
@@ -14,7 +14,7 @@ for n, d in sorted(r.items()):
     L.append("| %d | %.1f | %.3f | %.2f | %.1f | %.3f | %.2f | %.3f |" % (n, d["value"], d["value"] / r[1]["value"], d["ms_per_step"], d["e2e"]["value"],
                                                                       d["e2e"]["value"] / r[1]["e2e"]["value"], d["e2e"]["ms_per_step"], d["roofline"]["frac"]))
 L += ["", "Reference arm on the same boxes (oracle OpenMP port of the Rayon loop nest): 0.653 G pm/s on 16 cores (1-GPU box), 1.204 G pm/s on 32 cores (8-GPU box).", ""]
-for n in (2, 8):
+for n in (2, 4, 8):
     if n not in r or "in_process" not in r[n]:
         continue
     ip = r[n]["in_process"]
